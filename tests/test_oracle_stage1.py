@@ -1,0 +1,65 @@
+"""Pins the oracle's stage-1 restatement against the reference's own code (golden vectors made by
+tests/golden/make_golden.py from seg3d/core/voxel/voxel_generator.py and seg3d/ops/voxel_to_point)."""
+import hashlib
+import json
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from openseg3d_b200 import synthetic
+from oracle import oracle
+
+
+def sha(a):
+    return hashlib.sha256(np.ascontiguousarray(a).tobytes()).hexdigest()
+
+
+@pytest.mark.parametrize('name', ['cart_small', 'cyl_small', 'multi_small'])
+def test_voxelize_matches_reference_numba(golden_dir, name):
+    g = np.load(os.path.join(golden_dir, f'voxelize_{name}.npz'))
+    coors, ids = oracle.voxelize(g['points'], g['voxel_size'], g['pc_range'], has_batch=True)
+    assert np.array_equal(oracle.grid_size(g['voxel_size'], g['pc_range']), g['grid_size'])
+    assert coors.dtype == np.int32 and ids.dtype == np.int64
+    assert np.array_equal(coors, g['coors'])
+    assert np.array_equal(ids, g['point_voxel_ids'])
+    assert (ids == -1).sum() >= 16          # the fixture carries out-of-range points
+
+
+@pytest.mark.parametrize('name,sweeps,cyl', [('cart_full', 1, False), ('cyl_full', 1, True), ('multi_full', 3, False)])
+def test_voxelize_full_frame_checksums(golden_dir, name, sweeps, cyl):
+    sums = json.load(open(os.path.join(golden_dir, 'voxelize_full_checksums.json')))[name]
+    from tests.golden_cfg import CFG
+    cfg = CFG['cyl' if cyl else 'cart']
+    pts, _ = synthetic.make_batch([0], sweeps, cyl)
+    assert sha(pts) == sums['points'], 'synthetic generator drifted from the one the goldens were made with'
+    coors, ids = oracle.voxelize(pts, cfg['voxel_size'], cfg['pc_range'], has_batch=True)
+    assert coors.shape[0] == sums['m'] and pts.shape[0] == sums['n']
+    assert sha(coors) == sums['coors']
+    assert sha(ids) == sums['ids']
+
+
+def test_grid_sizes():
+    from tests.golden_cfg import CFG
+    assert oracle.grid_size(**CFG['cart']).tolist() == [1440, 1440, 64]
+    assert oracle.grid_size(**CFG['cyl']).tolist() == [1504, 524, 72]
+
+
+def test_voxel_to_point_matches_reference(golden_dir):
+    g = np.load(os.path.join(golden_dir, 'stage1_gather.npz'))
+    out = oracle.voxel_to_point(torch.from_numpy(g['feats']), torch.from_numpy(g['ids']))
+    assert torch.equal(out, torch.from_numpy(g['out']))
+
+
+def test_scatter_semantics():
+    feats = torch.tensor([[1., -2.], [3., 4.], [-5., -6.], [7., 8.]])
+    idx = torch.tensor([1, -1, 1, 0])
+    assert torch.equal(oracle.scatter_reduce(feats, idx, 'max'), torch.tensor([[7., 8.], [1., -2.]]))
+    assert torch.equal(oracle.scatter_reduce(feats, idx, 'mean'), torch.tensor([[7., 8.], [-2., -4.]]))
+    # empty rows: max -> 0 (torch_scatter fills rows nothing was scattered to with 0)
+    idx2 = torch.tensor([2, -1, 2, 0])
+    assert torch.equal(oracle.scatter_reduce(feats, idx2, 'max')[1], torch.zeros(2))
+    counts = torch.tensor([1, 2])
+    assert torch.allclose(oracle.voxel_avg_pooling(feats, torch.tensor([1, 5, 1, 0]), counts),
+                          torch.tensor([[7., 8.], [-2., -4.]]))
