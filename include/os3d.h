@@ -1,0 +1,196 @@
+/*
+ * os3d.h -- C ABI of libos3d.so, the B200 (sm_100a) implementation of OpenSeg3D's voxel-backbone hot path.
+ *
+ * This is the drop-in boundary: plain device pointers, sizes and a CUDA stream; no torch types.  The Python
+ * package openseg3d_b200 binds these with ctypes and mirrors the reference's module / operator API on top
+ * (INTEGRATION.md shows the binding a reference maintainer would add).  Every entry point
+ *   - is asynchronous on `stream` (a cudaStream_t passed as void*), never allocates, never synchronises;
+ *   - takes caller-owned scratch (sizes documented per call; the Python side gets it from torch's
+ *     caching allocator);
+ *   - returns 0 on success or a cudaError_t / negative os3d error code (os3d_error_string()).
+ *
+ * "replaces:" lines cite the reference interface (paths relative to the OpenSeg3D repository) that each
+ * entry point stands in for.
+ */
+#ifndef OS3D_H_
+#define OS3D_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define OS3D_ERR_BAD_ARG (-2)
+#define OS3D_KVOL 27 /* 3x3x3 kernel offsets, k = (kz*3+ky)*3+kx */
+
+/* One 16-byte open-addressing slot: linear voxel index -> row. key == -1 means empty. */
+typedef struct { int64_t key; int32_t val; int32_t aux; } os3d_slot_t;
+
+const char *os3d_error_string(int code);
+int os3d_version(void);
+
+/* ---------------------------------------------------------------- stage 1: voxelize / pool / gather --- */
+
+/* Scratch sizes for os3d_voxelize (bytes).  hash_cap is returned through *hash_cap (power of two >= 2n). */
+int os3d_voxelize_scratch(int64_t n, int64_t *hash_cap, int64_t *n_blocks);
+
+/* Dynamic voxelization with first-occurrence voxel ids.
+ * replaces: VoxelGenerator.generate / points_to_voxel (seg3d/core/voxel/voxel_generator.py:24-26,55-153), run per
+ *           frame inside WaymoDataset.prepare_data (seg3d/datasets/waymo_dataset.py:275), plus the batch column and
+ *           cumulative id offsets collate_batch adds (waymo_dataset.py:347-365).
+ * points  [n, stride] f32 rows (batch, x, y, z, ...) when has_batch, else (x, y, z, ...); frames contiguous, ascending.
+ * lo[3], vs[3]: range minimum and voxel size (f32, by value); grid[3] = (X, Y, Z) as the reference rounds it.
+ * table   [hash_cap] slots, slot_of [n] int32, block_sums [n_blocks + 1] int32 -- scratch.
+ * coors   [n, 4] int32 out (b, z, y, x), first *num_voxels rows valid;  pvid [n] int64 out (-1 = outside range).
+ * num_voxels: device int32[1].
+ */
+int os3d_voxelize(const float *points, int64_t n, int stride, int has_batch, float lo_x, float lo_y, float lo_z,
+                  float vs_x, float vs_y, float vs_z, int grid_x, int grid_y, int grid_z, os3d_slot_t *table,
+                  int64_t hash_cap, int32_t *slot_of, int32_t *block_sums, int64_t n_blocks, int32_t *coors,
+                  int64_t *pvid, int32_t *num_voxels, void *stream);
+
+/* Cylinder rows on device: out[i] = (rho, phi, z, x, y, rest...) from (x, y, z, rest...).
+ * replaces: cart2polar + concatenate (seg3d/utils/pointops_utils.py:8-11, seg3d/datasets/waymo_dataset.py:270-273).
+ * Not bit-exact with numpy's atan2 (last ulp); the bit-exact path feeds host-computed polar rows instead. */
+int os3d_cart2polar_rows(const float *in, int64_t n, int in_stride, int has_batch, float *out, void *stream);
+
+/* Point -> voxel scatter reductions; ids < 0 or >= m are skipped.
+ * replaces: VFE.forward -> torch_scatter.scatter(reduce='max'|'mean') (seg3d/models/voxel_encoders/vfe.py:24-25),
+ *           voxel_max_pooling / voxel_avg_pooling (seg3d/ops/voxel_pooling/voxel_pooling.py:62-79,10-41 and
+ *           src/voxel_pooling_cuda.cu:11-24).
+ * feats [n, c] f32; ids [n] int64; out [m, c] f32 (fully overwritten).  fix_empty: rows nothing was scattered to
+ * become 0 (torch_scatter semantics) at the price of one more pass; counts [m] int32 scratch (mean only; also an
+ * output: points per voxel).  counts_in (avg pooling with caller counts) may be NULL. */
+int os3d_scatter_max_f32(const float *feats, const int64_t *ids, int64_t n, int c, float *out, int64_t m, int fix_empty,
+                         void *stream);
+int os3d_scatter_mean_f32(const float *feats, const int64_t *ids, int64_t n, int c, float *out, int32_t *counts,
+                          const int32_t *counts_in, int64_t m, void *stream);
+/* argmax-free backward of scatter_max: grad_in[i] = grad_out[ids[i]] * (feats[i] == out[ids[i]]);  mean: /count */
+int os3d_scatter_max_bwd_f32(const float *grad_out, const float *feats, const float *out, const int64_t *ids, int64_t n,
+                             int c, int64_t m, float *grad_in, void *stream);
+int os3d_scatter_mean_bwd_f32(const float *grad_out, const int64_t *ids, const int32_t *counts, int64_t n, int c,
+                              int64_t m, float *grad_in, void *stream);
+
+/* Voxel -> point gather: out[i] = feats[ids[i]] or 0 when ids[i] < 0.  elem_size 4 (f32) or 2 (bf16).
+ * replaces: voxel_to_point (seg3d/ops/voxel_to_point/voxel_to_point.py:5-17). */
+int os3d_gather_rows(const void *feats, const int64_t *ids, int64_t n, int c, int elem_size, void *out, void *stream);
+/* backward of the gather = scatter-add of rows (f32). */
+int os3d_scatter_add_rows_f32(const float *grad_out, const int64_t *ids, int64_t n, int c, float *grad_feats, int64_t m,
+                              void *stream);
+
+/* ---------------------------------------------------------------- stage 2: kernel maps (rulebooks) --- */
+
+/* Insert rows of idx [m,4] (b,z,y,x) into an empty-initialised table (this call initialises it).
+ * replaces: spconv's hash-table build inside SubMConv3d / SparseConv3d (spconv-cu113, external). */
+int os3d_hash_build(const int32_t *idx, int64_t m, int sz, int sy, int sx, os3d_slot_t *table, int64_t cap, void *stream);
+
+/* Submanifold 3x3x3 neighbour table: nbr[i*27+k] = row j with coord[j] = coord[i] + (k - centre), else -1.
+ * pair_count: device int32[1] (number of valid pairs; diagnostic / FLOP accounting).
+ * replaces: spconv SubMConv3d indice-pair generation (call sites seg3d/models/backbones/pointtransformer.py:26,31,133). */
+int os3d_subm_table(const int32_t *idx, int64_t m, int sz, int sy, int sx, const os3d_slot_t *table, int64_t cap,
+                    int32_t *nbr, int32_t *pair_count, void *stream);
+
+/* Strided 3x3x3 / stride 2 / pad 1 output sites in ascending linear order.
+ * bitmap: [n_words] uint32 scratch over the dense output grid of the whole batch (n_words = ceil(B*oz*oy*ox/32) rounded up to a multiple of 4);
+ * word_prefix: [n_words] int32 out (exclusive popcount prefix -> O(1) site->row rank);  block_sums: [n_blocks+1] scratch.
+ * out_idx [<= cap_out, 4] int32;  num_out: device int32[1].
+ * replaces: spconv SparseConv3d output-index generation (seg3d/utils/spconv_utils.py:19; pointtransformer.py:159-166). */
+int os3d_strided_sites(const int32_t *idx, int64_t m, int batch, int oz, int oy, int ox, uint32_t *bitmap,
+                       int64_t n_words, int32_t *word_prefix, int32_t *block_sums, int64_t n_blocks, int32_t *out_idx,
+                       int64_t cap_out, int32_t *num_out, void *stream);
+
+/* Output-stationary tables of the strided conv and of its inverse:
+ *   fwd_nbr[o*27+k] = input row i with i = 2o - 1 + k (else -1)       SparseConv3d
+ *   inv_nbr[i*27+k] = output row o with the same pair (else -1)       SparseInverseConv3d
+ * replaces: spconv indice pairs of SparseConv3d and their swapped reuse by SparseInverseConv3d (spconv_utils.py:19,22). */
+int os3d_strided_tables(const int32_t *idx, int64_t m, int sz, int sy, int sx, const os3d_slot_t *table, int64_t cap,
+                        const int32_t *out_idx, int64_t m_out, int oz, int oy, int ox, const uint32_t *bitmap,
+                        const int32_t *word_prefix, int32_t *fwd_nbr, int32_t *inv_nbr, int32_t *pair_count, void *stream);
+
+/* ---------------------------------------------------------------- stage 3: sparse convolution --- */
+
+/* out[r, :] = bias + sum_k  in[nbr[r*27+k], :] . W[k]      (gather - GEMM, output-stationary: no scatter atomics)
+ * w: [27, cin, cout] (repacked from spconv's [cout, kz, ky, kx, cin] by os3d_pack_weight_*).
+ * replaces: SubMConv3d / SparseConv3d / SparseInverseConv3d forward (spconv-cu113; seg3d/utils/spconv_utils.py:16-22). */
+int os3d_spconv_fwd_f32(const float *in, const int32_t *nbr, int64_t m_out, int cin, int cout, const float *w,
+                        const float *bias, float *out, void *stream);
+/* bf16 in / bf16 out, f32 accumulate in TMEM on the tcgen05 tensor cores.  Fused epilogue: y = acc*scale[c]+shift[c]
+ * (bias and folded BatchNorm), optional residual add [m_out, cout] bf16, optional ReLU.  scale/shift (both or neither)
+ * and residual may be NULL.  in: rows of `cin` bf16 with cin % 8 == 0 (callers zero-pad); cout % 16 == 0, cout <= 512
+ * (cout % 32 == 0 above 256).  w: the image written by os3d_pack_weight_bf16(cin_pad = cin). */
+int os3d_spconv_fwd_bf16(const void *in, const int32_t *nbr, int64_t m_out, int cin, int cout, const void *w,
+                         const float *scale, const float *shift, const void *residual, int relu, void *out,
+                         void *stream);
+/* spconv 2.x weight [cout, kz, ky, kx, cin] f32 -> kernel layouts.  f32: [27, cin, cout].  bf16: the shared-memory image
+ * of the UMMA B operand, [ceil(27*cin_pad/64)][cout][128 B swizzled] (os3d_spconv_bf16_packed_elems elements). */
+int os3d_spconv_bf16_packed_elems(int cin_pad, int cout, int64_t *elems);
+int os3d_pack_weight_f32(const float *w_spconv, int cin, int cout, float *w_packed, void *stream);
+int os3d_pack_weight_bf16(const float *w_spconv, int cin, int cout, int cin_pad, void *w_packed, void *stream);
+
+/* ---------------------------------------------------------------- stage 4: window partition + attention --- */
+
+#define OS3D_MAX_LEVELS 4
+typedef struct {
+  int sparse_x, sparse_y, sparse_z;      /* voxel grid of this stage (x, y, z) */
+  int win_x, win_y, win_z;               /* window shape                        */
+  int nwin_x, nwin_y, nwin_z;            /* ceil(sparse/win) + 1                */
+  int shift_x, shift_y, shift_z;         /* per get_window_coors                */
+  int n_levels;
+  int lvl_lo[OS3D_MAX_LEVELS], lvl_hi[OS3D_MAX_LEVELS], lvl_tokens[OS3D_MAX_LEVELS];
+} os3d_window_cfg_t;
+
+/* Window partition of one shift, no host synchronisation.
+ * replaces: get_window_coors (seg3d/utils/swformer_utils.py:109-154), get_inner_win_inds
+ *           (seg3d/ops/ingroup_inds/src/ingroup_inds_cuda.cu:12-52), batching_single_shift
+ *           (seg3d/models/layers/point_transformer_layer.py:71-87), make_continuous_inds / get_flat2win_inds
+ *           (swformer_utils.py:8-31,158-171).
+ * idx [m,4] int32.  With n_win = batch * nwin_x*nwin_y*nwin_z dense window ids and n_blocks = ceil(n_win / 1024):
+ * scratch  win_count [n_win] int32, win_meta [n_win * 3] int32, block_sums [(n_blocks + 1) * 5] int32.
+ * Per-voxel outputs: win_id [m] int64 (batch_win_inds), in_win [m,3] int32 (z,y,x), level [m] int32 (-1 = occupancy
+ *   outside every batching range), win_rank [m] int32 (rank of the voxel's window among the windows of its level,
+ *   ascending window id = make_continuous_inds), inner [m] int32 (stable rank inside the window; the reference's
+ *   atomicAdd rank is a race, this is its deterministic member).  flat2window slot = win_rank * max_tokens + inner.
+ * Segment outputs: order [m] int32 = voxel rows grouped by window (ascending window id, ascending row inside);
+ *   seg_start / seg_len [<= m + 1] int32: one entry per non-empty window, level-major (all level-0 windows first),
+ *   ascending window id inside a level;
+ *   level_info: device int32[16] = { n_windows[4], first_window[4], 0,0,0,0, tokens_outside_ranges, n_windows_total,
+ *   n_tokens_assigned, tokens_over_capacity }.  (The reference drops over-capacity tokens and then cannot continue
+ *   -- SURVEY.md Appendix C; callers treat a non-zero count as an error.) */
+int os3d_window_partition(const int32_t *idx, int64_t m, int batch, const os3d_window_cfg_t *cfg, int32_t *win_count,
+                          int32_t *win_meta, int32_t *block_sums, int64_t n_blocks, int64_t *win_id, int32_t *in_win,
+                          int32_t *level, int32_t *win_rank, int32_t *inner, int32_t *order, int32_t *seg_start,
+                          int32_t *seg_len, int32_t *level_info, void *stream);
+
+/* The same partition over caller-supplied group ids in [0, n_groups) (cfg supplies only the batching levels).
+ * replaces: get_inner_win_inds as a stand-alone op (seg3d/ops/ingroup_inds/ingroup_inds.py:7-20): `inner` is the rank. */
+int os3d_group_partition(const int64_t *group, int64_t n, int64_t n_groups, const os3d_window_cfg_t *cfg, int32_t *count,
+                         int32_t *meta, int32_t *block_sums, int64_t n_blocks, int32_t *level, int32_t *group_rank,
+                         int32_t *inner, int32_t *order, int32_t *seg_start, int32_t *seg_len, int32_t *level_info,
+                         void *stream);
+
+/* Sinusoidal window position embedding, flat [m, c] (f32 or bf16 by elem_size).
+ * replaces: SparseWindowPartitionLayer.get_pos_embed (point_transformer_layer.py:152-207). */
+int os3d_pos_embed(const int32_t *in_win, int64_t m, int c, int win_x, int win_y, int win_z, float temperature,
+                   int elem_size, void *out, void *stream);
+
+/* In-place L2 normalisation of every head slice of q and k rows (F.normalize, eps 1e-12).
+ * replaces: cosine_msa.py:152-153. */
+int os3d_qk_normalize(void *q, void *k, int64_t ld, int64_t m, int c, int heads, int elem_size, void *stream);
+
+/* Variable-length cosine window attention over the segments of os3d_window_partition.
+ * q, k: [m] rows with pitch ld (elements), already head-normalised; v: pitch ldv; heads*d == c.  Per (window, head):
+ *   softmax( q k^T / max(tau, tau_min) ) v        -- no padding, no masks, no score tensor in memory.
+ * tau: device f32[1];  lvl_tokens: host int[4] (max_tokens per batching level, sizes the work decomposition).
+ * out [m, c] in the original voxel order.  elem_size 4 (f32) or 2 (bf16).
+ * replaces: flat2window + CosineMultiheadAttention core + window2flat (swformer_utils.py:34-85,
+ *           seg3d/models/layers/cosine_msa.py:115-177, point_transformer_layer.py:233-258). */
+int os3d_window_attention(const void *q, const void *k, const void *v, int64_t ld, int64_t ldv, int64_t m, int c, int heads,
+                          const int32_t *order, const int32_t *seg_start, const int32_t *seg_len,
+                          const int32_t *level_info, const int *lvl_tokens, const float *tau, float tau_min,
+                          int elem_size, void *out, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* OS3D_H_ */

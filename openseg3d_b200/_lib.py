@@ -1,0 +1,115 @@
+"""ctypes binding of libos3d.so (the C ABI declared in include/os3d.h).
+
+There is no CPU fallback and no alternative backend: if the shared library is missing or a call fails the
+error is raised immediately (the north star's "fail loudly").  Tensors are passed as raw device pointers,
+the stream is torch's current CUDA stream, scratch comes from torch's caching allocator.
+"""
+import ctypes
+import os
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, 'libos3d.so')
+
+I32, I64, F32, PTR = ctypes.c_int, ctypes.c_int64, ctypes.c_float, ctypes.c_void_p
+
+
+class WindowCfg(ctypes.Structure):
+    """os3d_window_cfg_t"""
+    _fields_ = [(n, ctypes.c_int) for n in
+                ['sparse_x', 'sparse_y', 'sparse_z', 'win_x', 'win_y', 'win_z', 'nwin_x', 'nwin_y', 'nwin_z',
+                 'shift_x', 'shift_y', 'shift_z', 'n_levels']] + \
+               [('lvl_lo', ctypes.c_int * 4), ('lvl_hi', ctypes.c_int * 4), ('lvl_tokens', ctypes.c_int * 4)]
+
+
+# name -> argtypes (the trailing stream argument included); every function returns int
+SIGNATURES = {
+    'os3d_voxelize_scratch': [I64, ctypes.POINTER(I64), ctypes.POINTER(I64)],
+    'os3d_spconv_bf16_packed_elems': [I32, I32, ctypes.POINTER(I64)],
+    'os3d_voxelize': [PTR, I64, I32, I32, F32, F32, F32, F32, F32, F32, I32, I32, I32, PTR, I64, PTR, PTR, I64, PTR, PTR,
+                      PTR, PTR],
+    'os3d_cart2polar_rows': [PTR, I64, I32, I32, PTR, PTR],
+    'os3d_scatter_max_f32': [PTR, PTR, I64, I32, PTR, I64, I32, PTR],
+    'os3d_scatter_mean_f32': [PTR, PTR, I64, I32, PTR, PTR, PTR, I64, PTR],
+    'os3d_scatter_max_bwd_f32': [PTR, PTR, PTR, PTR, I64, I32, I64, PTR, PTR],
+    'os3d_scatter_mean_bwd_f32': [PTR, PTR, PTR, I64, I32, I64, PTR, PTR],
+    'os3d_gather_rows': [PTR, PTR, I64, I32, I32, PTR, PTR],
+    'os3d_scatter_add_rows_f32': [PTR, PTR, I64, I32, PTR, I64, PTR],
+    'os3d_hash_build': [PTR, I64, I32, I32, I32, PTR, I64, PTR],
+    'os3d_subm_table': [PTR, I64, I32, I32, I32, PTR, I64, PTR, PTR, PTR],
+    'os3d_strided_sites': [PTR, I64, I32, I32, I32, I32, PTR, I64, PTR, PTR, I64, PTR, I64, PTR, PTR],
+    'os3d_strided_tables': [PTR, I64, I32, I32, I32, PTR, I64, PTR, I64, I32, I32, I32, PTR, PTR, PTR, PTR, PTR, PTR],
+    'os3d_spconv_fwd_f32': [PTR, PTR, I64, I32, I32, PTR, PTR, PTR, PTR],
+    'os3d_spconv_fwd_bf16': [PTR, PTR, I64, I32, I32, PTR, PTR, PTR, PTR, I32, PTR, PTR],
+    'os3d_pack_weight_f32': [PTR, I32, I32, PTR, PTR],
+    'os3d_pack_weight_bf16': [PTR, I32, I32, I32, PTR, PTR],
+    'os3d_window_partition': [PTR, I64, I32, ctypes.POINTER(WindowCfg), PTR, PTR, PTR, I64, PTR, PTR, PTR, PTR, PTR, PTR,
+                              PTR, PTR, PTR, PTR],
+    'os3d_group_partition': [PTR, I64, I64, ctypes.POINTER(WindowCfg), PTR, PTR, PTR, I64, PTR, PTR, PTR, PTR, PTR, PTR, PTR,
+                             PTR],
+    'os3d_pos_embed': [PTR, I64, I32, I32, I32, I32, F32, I32, PTR, PTR],
+    'os3d_qk_normalize': [PTR, PTR, I64, I64, I32, I32, I32, PTR],
+    'os3d_window_attention': [PTR, PTR, PTR, I64, I64, I64, I32, I32, PTR, PTR, PTR, PTR, ctypes.POINTER(ctypes.c_int * 4), PTR,
+                              F32, I32, PTR, PTR],
+}
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise ImportError(f'{LIB_PATH} is missing: build it with `python openseg3d_b200/csrc/build.py` '
+                              '(nvcc, sm_100a). openseg3d_b200 has no CPU or PyTorch fallback.')
+        L = ctypes.CDLL(LIB_PATH)
+        for name, argtypes in SIGNATURES.items():
+            fn = getattr(L, name)          # AttributeError here = header / library mismatch: fail loudly
+            fn.argtypes = argtypes
+            fn.restype = ctypes.c_int
+        L.os3d_error_string.restype = ctypes.c_char_p
+        L.os3d_error_string.argtypes = [ctypes.c_int]
+        _lib = L
+    return _lib
+
+
+def exported_symbols():
+    return sorted(SIGNATURES) + ['os3d_error_string', 'os3d_version']
+
+
+def ptr(t):
+    """Device pointer of a tensor (None -> NULL).  The tensor must be contiguous."""
+    if t is None:
+        return None
+    assert t.is_contiguous(), 'os3d kernels take contiguous tensors'
+    return t.data_ptr()
+
+
+def stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+_launches = 0
+
+
+def launches():
+    """Number of libos3d entry-point calls so far (bench.py reports it as its kernel-launch evidence)."""
+    return _launches
+
+
+def call(name, *args):
+    """Invoke an entry point on torch's current stream; raise RuntimeError on a non-zero status."""
+    global _launches
+    L = lib()
+    conv = [ptr(a) if isinstance(a, torch.Tensor) else a for a in args]
+    rc = getattr(L, name)(*conv, stream())
+    _launches += 1
+    if rc != 0:
+        raise RuntimeError(f'{name} failed: {L.os3d_error_string(rc).decode()} (code {rc})')
+
+
+def require_cuda(*tensors):
+    for t in tensors:
+        if t is not None and not t.is_cuda:
+            raise RuntimeError('openseg3d_b200 ops take CUDA tensors (there is no CPU path)')

@@ -1,0 +1,337 @@
+"""Stage 4 modules: sparse window partition, cosine window attention, SWFormer block.
+
+Class names, constructor arguments, forward signatures and state_dict keys mirror
+seg3d/models/layers/point_transformer_layer.py:11-339 and seg3d/models/layers/cosine_msa.py:413-501, so a reference
+checkpoint loads unchanged and PointTransformer can be written exactly as in the reference.  What differs is the
+execution: windows are never padded to [R, T, C]; the partition layer emits window SEGMENTS over the flat voxel list
+(no host sync) and attention runs variable-length over them (libos3d: os3d_window_partition, os3d_window_attention).
+The padded per-level view the reference exposes (flat2win inds, padded pos-embed, key masks) is still available
+through ``materialize()`` for callers and tests that want it.
+"""
+import ctypes
+
+import numpy as np
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from .. import _lib
+from .._lib import WindowCfg
+from ..ops.pooling import scatter_mean
+
+
+class WindowSegments(object):
+    """Device-side result of one shift's partition (see include/os3d.h: os3d_window_partition)."""
+
+    def __init__(self, cfg, batching_info, m):
+        self.cfg, self.batching_info, self.m = cfg, batching_info, m
+        self.lvl_tokens = (ctypes.c_int * 4)(*[cfg.lvl_tokens[i] for i in range(4)])
+
+    def check_no_drop(self):
+        """One host read: raises if any token would be dropped (the reference cannot continue either, App. C)."""
+        info = self.level_info.cpu()
+        if int(info[12]) or int(info[15]):
+            raise RuntimeError(f'window batching would drop {int(info[12]) + int(info[15])} tokens; unsupported '
+                               '(the reference desyncs features and indices in that case)')
+        return info
+
+
+class Flat2WinInds(dict):
+    """``flat2win_inds_shift{i}``: carries the segment representation under string keys ('segments',
+    'voxel_batching_level', 'batching_info'); ``materialize()`` adds the reference's per-level entries
+    {level: (flat2window_inds, torch.where(mask))} (swformer_utils.py:8-31) -- that costs a host sync per level, which is
+    why the hot path does not use them."""
+
+    def materialize(self):
+        seg = self['segments']
+        lvl, rank, inner = seg.level, seg.win_rank.long(), seg.inner.long()
+        for bl in seg.batching_info:
+            mask = lvl == bl
+            if not bool(mask.any()):
+                continue
+            t = seg.batching_info[bl]['max_tokens']
+            self[bl] = (rank[mask] * t + inner[mask], torch.where(mask))
+        return self
+
+    def levels(self):
+        return {k: v for k, v in self.items() if not isinstance(k, str)}
+
+
+def flat2window(feat, inds):
+    """Reference-layout scatter [M, C] -> {level: [R, T, C]} (swformer_utils.py:34-64); test / API helper."""
+    if not inds.levels():
+        inds.materialize()
+    binfo = inds['batching_info']
+    out = {}
+    for bl, (slot, where) in inds.levels().items():
+        t = binfo[bl]['max_tokens']
+        r = int(torch.div(slot, t, rounding_mode='floor').max().item()) + 1
+        buf = torch.zeros((r * t, feat.shape[-1]), dtype=feat.dtype, device=feat.device)
+        buf[slot] = feat[where[0]]
+        out[bl] = buf.reshape(r, t, -1)
+    return out
+
+
+def window2flat(feat_3d_dict, inds):
+    """Inverse of flat2window (swformer_utils.py:67-85)."""
+    first = next(iter(feat_3d_dict.values()))
+    n = sum(v[0].shape[0] for v in inds.levels().values())
+    out = torch.zeros((n, first.shape[-1]), dtype=first.dtype, device=first.device)
+    for bl, f in feat_3d_dict.items():
+        slot, where = inds[bl]
+        out[where[0]] = f.reshape(-1, f.shape[-1])[slot]
+    return out
+
+
+class SparseWindowPartitionLayer(nn.Module):
+    """Same constructor and output keys as point_transformer_layer.py:11-69.  forward(x) -> dict with
+    batch_win_inds_shift{0,1}, coors_in_win_shift{0,1}, voxel_features, voxel_coords, voxel_keep_inds,
+    voxel_batching_level_shift{0,1}, flat2win_inds_shift{0,1}, pos_dict_shift{0,1}, key_mask_shift{0,1}."""
+
+    def __init__(self, batching_info, window_shape, sparse_shape, normalize_pos=False, pos_temperature=1000):
+        super().__init__()
+        if normalize_pos:
+            raise NotImplementedError('normalize_pos=True is never used by the reference model')
+        if len(window_shape) != 3:
+            raise NotImplementedError('3-D windows only (the reference model uses [10, 10, 8])')
+        self.batching_info = batching_info
+        self.sparse_shape = sparse_shape
+        self.window_shape = window_shape
+        self.normalize_pos = normalize_pos
+        self.pos_temperature = pos_temperature
+
+    def _cfg(self, do_shift):
+        """get_window_coors' scalar setup, swformer_utils.py:109-131."""
+        wx, wy, wz = [int(w) for w in self.window_shape]
+        sx, sy, sz = [float(s) for s in self.sparse_shape]
+        assert sz < sx, 'Usually holds... in case of wrong order'
+        cfg = WindowCfg()
+        cfg.sparse_x, cfg.sparse_y, cfg.sparse_z = int(sx), int(sy), int(sz)
+        cfg.win_x, cfg.win_y, cfg.win_z = wx, wy, wz
+        cfg.nwin_x, cfg.nwin_y, cfg.nwin_z = [int(np.ceil(s / w) + 1) for s, w in ((sx, wx), (sy, wy), (sz, wz))]
+        shift = (wx // 2, wy // 2, wz // 2) if do_shift else (wx, wy, wz)
+        cfg.shift_x, cfg.shift_y = shift[0], shift[1]
+        cfg.shift_z = 0 if sz == wz else shift[2]
+        levels = sorted(self.batching_info)
+        if len(levels) > 4 or levels != list(range(len(levels))):
+            raise NotImplementedError('batching levels must be 0..n-1 with n <= 4')
+        cfg.n_levels = len(levels)
+        for i, bl in enumerate(levels):
+            cfg.lvl_lo[i], cfg.lvl_hi[i] = [int(v) for v in self.batching_info[bl]['batching_range']]
+            cfg.lvl_tokens[i] = int(self.batching_info[bl]['max_tokens'])
+        return cfg
+
+    @torch.no_grad()
+    def partition(self, indices, batch_size, do_shift):
+        indices = indices.int().contiguous() if indices.dtype != torch.int32 else indices.contiguous()
+        m, dev = indices.shape[0], indices.device
+        cfg = self._cfg(do_shift)
+        n_win = batch_size * cfg.nwin_x * cfg.nwin_y * cfg.nwin_z
+        nb = (n_win + 1023) // 1024
+        i32 = dict(dtype=torch.int32, device=dev)
+        seg = WindowSegments(cfg, self.batching_info, m)
+        seg.win_id = torch.empty(m, dtype=torch.int64, device=dev)
+        seg.in_win = torch.empty((m, 3), **i32)
+        seg.level, seg.win_rank, seg.inner = torch.empty(m, **i32), torch.empty(m, **i32), torch.empty(m, **i32)
+        seg.order = torch.empty(m, **i32)
+        seg.seg_start, seg.seg_len = torch.empty(m + 1, **i32), torch.empty(m + 1, **i32)
+        seg.level_info = torch.empty(16, **i32)
+        win_count, win_meta = torch.empty(n_win, **i32), torch.empty(n_win * 3, **i32)
+        block_sums = torch.empty((nb + 1) * 5, **i32)
+        _lib.call('os3d_window_partition', indices, m, batch_size, ctypes.byref(cfg), win_count, win_meta, block_sums, nb,
+                  seg.win_id, seg.in_win, seg.level, seg.win_rank, seg.inner, seg.order, seg.seg_start, seg.seg_len,
+                  seg.level_info)
+        return seg
+
+    @torch.no_grad()
+    def get_pos_embed(self, seg, feat_dim, dtype):
+        """Flat [M, C] sinusoidal embedding of the in-window coordinates (point_transformer_layer.py:152-205)."""
+        out = torch.empty((seg.m, feat_dim), dtype=dtype, device=seg.in_win.device)
+        wx, wy, wz = [int(w) for w in self.window_shape]
+        _lib.call('os3d_pos_embed', seg.in_win, seg.m, feat_dim, wx, wy, wz, float(self.pos_temperature),
+                  out.element_size(), out)
+        return out
+
+    def forward(self, x):
+        feats, indices = x.features, x.indices
+        batch_size = getattr(x, 'batch_size', None)
+        if batch_size is None:
+            batch_size = int(indices[:, 0].max().item()) + 1
+        info = {'voxel_features': feats, 'voxel_coords': indices.long()}
+        m = indices.shape[0]
+        info['voxel_keep_inds'] = torch.arange(m, device=indices.device, dtype=torch.long)   # nothing is ever dropped
+        for i in range(2):
+            seg = self.partition(indices, batch_size, i == 1)
+            info[f'batch_win_inds_shift{i}'] = seg.win_id
+            info[f'coors_in_win_shift{i}'] = seg.in_win
+            info[f'voxel_batching_level_shift{i}'] = seg.level
+            info[f'flat2win_inds_shift{i}'] = Flat2WinInds(segments=seg, voxel_batching_level=seg.level,
+                                                           batching_info=self.batching_info)
+            info[f'pos_dict_shift{i}'] = {'flat': self.get_pos_embed(seg, feats.shape[1], feats.dtype)}
+            info[f'key_mask_shift{i}'] = {}     # padding masks are implicit in the segment lengths
+        return info
+
+
+class CosineMultiheadAttention(nn.MultiheadAttention):
+    """Parameters identical to the reference subclass (cosine_msa.py:413-431): in_proj_weight / in_proj_bias /
+    out_proj.{weight,bias} from nn.MultiheadAttention plus the shared temperature ``tau`` [1, 1, 1]."""
+
+    def __init__(self, embed_dim, num_heads, dropout=0., bias=True, batch_first=False, cosine=True, tau_min=0.01,
+                 non_shared_tau=False):
+        super().__init__(embed_dim, num_heads, dropout, bias)
+        if not cosine or non_shared_tau:
+            raise NotImplementedError('only the shared-tau cosine attention the reference model builds')
+        self.tau_min = tau_min
+        self.tau = nn.Parameter(torch.ones(1, 1, 1))
+        self._cast = {}
+
+    def params(self, dtype):
+        """(in_proj_weight, in_proj_bias, out_proj.weight, out_proj.bias) in the compute dtype, cached."""
+        if dtype == self.in_proj_weight.dtype:
+            return self.in_proj_weight, self.in_proj_bias, self.out_proj.weight, self.out_proj.bias
+        tag = (dtype, self.in_proj_weight._version, self.out_proj.weight._version, self.in_proj_weight.data_ptr())
+        if self._cast.get('tag') != tag:
+            self._cast = {'tag': tag, 'p': tuple(p.detach().to(dtype) for p in (
+                self.in_proj_weight, self.in_proj_bias, self.out_proj.weight, self.out_proj.bias))}
+        return self._cast['p']
+
+    def forward_segments(self, feat, pos, seg):
+        """feat, pos: flat [M, C]; seg: WindowSegments.  Returns [M, C]."""
+        if self.training and self.dropout > 0:
+            raise NotImplementedError('attention dropout (training) is not built yet')
+        m, c = feat.shape
+        w_in, b_in, w_out, b_out = self.params(feat.dtype)
+        qk_in = feat + pos if pos is not None else feat
+        qk = F.linear(qk_in, w_in[:2 * c], b_in[:2 * c])           # [M, 2C]: q | k   (q = k = x + pos)
+        v = F.linear(feat, w_in[2 * c:], b_in[2 * c:])             # [M, C]           (v = x)
+        es = feat.element_size()
+        k_ptr = qk.data_ptr() + c * es                            # k = columns [C, 2C) of the same rows
+        _lib.call('os3d_qk_normalize', qk, k_ptr, 2 * c, m, c, self.num_heads, es)
+        out = torch.empty((m, c), dtype=feat.dtype, device=feat.device)
+        _lib.call('os3d_window_attention', qk, k_ptr, v, 2 * c, c, m, c, self.num_heads, seg.order, seg.seg_start,
+                  seg.seg_len, seg.level_info, ctypes.byref(seg.lvl_tokens), self.tau.detach().float().reshape(1),
+                  float(self.tau_min), es, out)
+        return F.linear(out, w_out, b_out)
+
+
+class WindowAttention(nn.Module):
+    def __init__(self, d_model, nhead, attn_drop, cosine=True, tau_min=0.01):
+        super().__init__()
+        self.self_attn = CosineMultiheadAttention(d_model, nhead, dropout=attn_drop, batch_first=False, tau_min=tau_min,
+                                                  cosine=cosine, non_shared_tau=False)
+
+    def forward(self, feat_2d, pos_dict, ind_dict, key_padding_dict=None):
+        """Same call as the reference (point_transformer_layer.py:233): feat_2d [M, C]; pos_dict / ind_dict are the
+        partition layer's pos_dict_shift{i} / flat2win_inds_shift{i}; key_padding_dict is unused (no padding exists)."""
+        if feat_2d.dtype not in (torch.float32, torch.bfloat16):
+            raise RuntimeError('window attention runs in float32 or bfloat16')
+        pos = pos_dict['flat'] if pos_dict is not None else None
+        if pos is not None and pos.dtype != feat_2d.dtype:
+            pos = pos.to(feat_2d.dtype)
+        return self.self_attn.forward_segments(feat_2d.contiguous(), pos, ind_dict['segments'])
+
+
+def _cast_like(mod, name, dtype):
+    p = getattr(mod, name)
+    if p is None or p.dtype == dtype:
+        return p
+    cache = mod.__dict__.setdefault('_os3d_cast', {})
+    tag = (dtype, p._version, p.data_ptr())
+    hit = cache.get(name)
+    if hit is None or hit[0] != tag:
+        hit = (tag, p.detach().to(dtype))
+        cache[name] = hit
+    return hit[1]
+
+
+def linear_in(mod, x):
+    """nn.Linear applied in x's dtype (cached weight copies) -- explicit bf16 instead of autocast."""
+    return F.linear(x, _cast_like(mod, 'weight', x.dtype), _cast_like(mod, 'bias', x.dtype))
+
+
+def layer_norm_in(mod, x):
+    return F.layer_norm(x, mod.normalized_shape, _cast_like(mod, 'weight', x.dtype), _cast_like(mod, 'bias', x.dtype),
+                        mod.eps)
+
+
+class MLP(nn.Module):
+    def __init__(self, in_features, hidden_features=None, out_features=None, drop=0.):
+        super().__init__()
+        out_features = out_features or in_features
+        hidden_features = hidden_features or in_features
+        self.fc1 = nn.Linear(in_features, hidden_features)
+        self.act = nn.GELU()
+        self.fc2 = nn.Linear(hidden_features, out_features)
+        self.drop = nn.Dropout(drop)
+
+    def forward(self, x):
+        return self.drop(linear_in(self.fc2, self.drop(self.act(linear_in(self.fc1, x)))))
+
+
+class DropPath(nn.Module):
+    """Stochastic depth per row (seg3d/models/layers/drop.py:4-34); identity at inference."""
+
+    def __init__(self, drop_prob=0., scale_by_keep=True):
+        super().__init__()
+        self.drop_prob, self.scale_by_keep = drop_prob, scale_by_keep
+
+    def forward(self, x):
+        if self.drop_prob == 0. or not self.training:
+            return x
+        keep = 1 - self.drop_prob
+        mask = x.new_empty((x.shape[0],) + (1,) * (x.ndim - 1)).bernoulli_(keep)
+        if keep > 0.0 and self.scale_by_keep:
+            mask.div_(keep)
+        return x * mask
+
+
+class EncoderLayer(nn.Module):
+    """Post-norm residual layer, point_transformer_layer.py:278-298."""
+
+    def __init__(self, d_model, nhead, mlp_hidden_dim=256, drop=0., attn_drop=0.1, drop_path=0.):
+        super().__init__()
+        self.win_attn = WindowAttention(d_model, nhead, attn_drop)
+        self.norm1 = nn.LayerNorm(d_model)
+        self.norm2 = nn.LayerNorm(d_model)
+        self.drop_path = DropPath(drop_path) if drop_path > 0. else nn.Identity()
+        self.mlp = MLP(in_features=d_model, hidden_features=mlp_hidden_dim, drop=drop)
+
+    def forward(self, x, pos_dict, ind_dict, key_padding_mask_dict=None):
+        x = x + self.drop_path(layer_norm_in(self.norm1, self.win_attn(x, pos_dict, ind_dict, key_padding_mask_dict)))
+        return x + self.drop_path(layer_norm_in(self.norm2, self.mlp(x)))
+
+
+class SWFormerBlock(nn.Module):
+    """depth encoder layers: the first depth//2 on the unshifted windows, the rest on the half-window shift
+    (point_transformer_layer.py:300-339)."""
+
+    def __init__(self, d_model, nhead, depth=4, mlp_ratio=2., attn_drop=0.1, drop=0., drop_path=0.):
+        super().__init__()
+        self.depth = depth
+        self.layers = nn.ModuleList([
+            EncoderLayer(d_model, nhead, int(d_model * mlp_ratio), attn_drop=attn_drop, drop=drop,
+                         drop_path=drop_path[i] if isinstance(drop_path, list) else drop_path) for i in range(depth)])
+
+    def forward(self, batch_dict, using_checkpoint=True):
+        x = batch_dict['voxel_features']
+        for i, layer in enumerate(self.layers):
+            s = 0 if i < int(self.depth / 2) else 1
+            x = layer(x, batch_dict[f'pos_dict_shift{s}'], batch_dict[f'flat2win_inds_shift{s}'],
+                      batch_dict[f'key_mask_shift{s}'])
+        return x
+
+
+class FlattenSELayer(nn.Module):
+    """Per-sample squeeze-excite over flat rows (seg3d/models/layers/se_layer.py:6-30); the scatter(mean) over the
+    batch index goes through libos3d instead of torch_scatter."""
+
+    def __init__(self, channel, reduction=4):
+        super().__init__()
+        self.fc = nn.Sequential(nn.Linear(channel, channel // reduction, bias=False), nn.ReLU(inplace=True),
+                                nn.Linear(channel // reduction, channel, bias=False), nn.Sigmoid())
+
+    def forward(self, x, indices, batch_size=None):
+        indices = indices.long()
+        pooled = scatter_mean(x, indices, batch_size)
+        gate = self.fc(pooled.to(x.dtype))
+        return x * gate[indices]

@@ -1,0 +1,163 @@
+"""Segformer segmentor (seg3d/models/segmentors/segformer.py:12-146): point MLP -> VFE scatter -> PointTransformer ->
+voxel_to_point gather -> fusion MLP -> SE -> classifier.  Same module tree / state_dict keys as the reference.
+
+Two additions for the B200 path, both optional so that reference-shaped batch dicts keep working:
+  * if the batch has no 'point_voxel_ids' the raw points are voxelized on the GPU as the first step of forward
+     -- the reference does this per frame in DataLoader workers;
+  * ``compute_dtype=torch.bfloat16`` runs the backbone in bf16 (tcgen05 sparse conv, bf16 attention) and the point
+    MLPs under bf16 autocast; voxelization and pooling always stay fp32.
+"""
+from collections import OrderedDict
+from types import SimpleNamespace
+
+import numpy as np
+import torch
+import torch.nn as nn
+
+from ..core.voxel import voxelize_batch, _geometry
+from ..ops import voxel_to_point
+from .backbones import PointTransformer
+from .layers import FlattenSELayer
+from .voxel_encoders import VFE
+
+
+class Segformer(nn.Module):
+    def __init__(self, dataset, batching_info, window_shape, depths, drop_path_rate, compute_dtype=torch.float32):
+        super().__init__()
+        dim_point = dataset.dim_point + (2 if dataset.use_cylinder else 0)
+        self.compute_dtype = compute_dtype
+        self.voxel_size, self.point_cloud_range = dataset.voxel_size, dataset.point_cloud_range
+
+        self.point_feature_channel = 64
+        self.point_encoder = nn.Sequential(
+            nn.BatchNorm1d(dim_point),
+            nn.Linear(dim_point, 64, bias=False), nn.BatchNorm1d(64), nn.ReLU(inplace=True),
+            nn.Linear(64, 128, bias=False), nn.BatchNorm1d(128), nn.ReLU(inplace=True),
+            nn.Linear(128, 256, bias=False), nn.BatchNorm1d(256), nn.ReLU(inplace=True),
+            nn.Linear(256, self.point_feature_channel))
+
+        self.use_multi_sweeps = dataset.use_multi_sweeps
+        self.vfe = VFE(dim_point, reduce='mean') if self.use_multi_sweeps else VFE(self.point_feature_channel, reduce='max')
+        self.scatter = VFE(3, reduce='mean')          # present (parameter-free) in the reference too, never called
+
+        self.voxel_in_feature_channel = self.vfe.voxel_feature_channel
+        self.voxel_feature_channel = 32
+        self.point_transformer = PointTransformer(self.voxel_in_feature_channel, self.voxel_feature_channel,
+                                                  dataset.grid_size, dataset.voxel_size, dataset.point_cloud_range,
+                                                  batching_info=batching_info, window_shape=window_shape, depths=depths,
+                                                  drop_path_rate=drop_path_rate, num_classes=dataset.num_classes)
+        if dataset.use_image_feature:
+            raise NotImplementedError('image-feature fusion is off in every reference config (config.py:17)')
+        self.use_image_feature = False
+        self.image_feature_channel = 0
+
+        self.fusion_feature_channel = 64
+        self.fusion_encoder = nn.Sequential(
+            nn.Linear(self.point_feature_channel + self.voxel_feature_channel, 256, bias=False), nn.BatchNorm1d(256),
+            nn.ReLU(inplace=True),
+            nn.Linear(256, 128, bias=False), nn.BatchNorm1d(128), nn.ReLU(inplace=True),
+            nn.Linear(128, self.fusion_feature_channel, bias=False), nn.BatchNorm1d(self.fusion_feature_channel),
+            nn.ReLU(inplace=True))
+        self.se = FlattenSELayer(self.fusion_feature_channel)
+        self.classifier = nn.Sequential(nn.Linear(self.fusion_feature_channel, 64, bias=False), nn.BatchNorm1d(64),
+                                        nn.ReLU(True), nn.Dropout(0.3),
+                                        nn.Linear(64, dataset.num_classes, bias=False))
+        self.weight_initialization()
+
+    def weight_initialization(self):
+        for m in self.modules():
+            if isinstance(m, (nn.Linear, nn.Conv2d)):
+                nn.init.kaiming_normal_(m.weight)
+                if m.bias is not None:
+                    nn.init.constant_(m.bias, 0)
+            elif isinstance(m, (nn.BatchNorm1d, nn.BatchNorm2d)):
+                nn.init.constant_(m.weight, 1)
+                if m.bias is not None:
+                    nn.init.constant_(m.bias, 0)
+            elif isinstance(m, nn.LayerNorm):
+                nn.init.constant_(m.weight, 1.0)
+                nn.init.constant_(m.bias, 0)
+
+    def forward(self, batch_dict):
+        raw = batch_dict['points']
+        bf16 = self.compute_dtype == torch.bfloat16
+        if 'point_voxel_ids' not in batch_dict:            # voxelize in the forward
+            coords, pvid = voxelize_batch(raw, self.voxel_size, self.point_cloud_range, has_batch=True)
+            batch_dict['voxel_coords'], batch_dict['point_voxel_ids'] = coords, pvid
+        points = raw[:, 1:]
+        point_voxel_ids = batch_dict['point_voxel_ids']
+        num_voxels = batch_dict['voxel_coords'].shape[0]
+        if self.use_multi_sweeps:
+            cur_point_indices = points[:, 3] == 0
+            cur_points = points[cur_point_indices]
+        else:
+            cur_points = points
+        with torch.autocast('cuda', dtype=torch.bfloat16, enabled=bf16):
+            point_per_features = self.point_encoder(cur_points)
+
+        # encode voxel features (fp32 pooling)
+        if self.use_multi_sweeps:
+            voxel_features = self.vfe(points, point_voxel_ids, num_voxels)
+        else:
+            voxel_features = self.vfe(point_per_features, point_voxel_ids, num_voxels)
+        batch_dict['voxel_features'] = voxel_features.to(self.compute_dtype)
+        batch_dict = self.point_transformer(batch_dict)
+
+        # point features from the encoded voxel features
+        ids = point_voxel_ids[cur_point_indices] if self.use_multi_sweeps else point_voxel_ids
+        point_voxel_features = voxel_to_point(batch_dict['voxel_features'], ids)
+        with torch.autocast('cuda', dtype=torch.bfloat16, enabled=bf16):
+            fused = torch.cat([point_per_features.to(point_voxel_features.dtype), point_voxel_features], dim=1)
+            fused = self.fusion_encoder(fused)
+            batch_idx = raw[:, 0][cur_point_indices] if self.use_multi_sweeps else raw[:, 0]
+            fused = fused + self.se(fused, batch_idx, batch_dict['batch_size'])
+            point_out = self.classifier(fused)
+
+        result = OrderedDict()
+        result['point_out'] = point_out
+        result['voxel_out'] = batch_dict['voxel_out']
+        result['aux_voxel_out'] = batch_dict['aux_voxel_out']
+        result['voxel_coords'] = batch_dict['voxel_coords']
+        result['aux_voxel_coords'] = batch_dict['aux_voxel_coords']
+        return result
+
+
+def default_batching_info():
+    """cfg.MODEL.BATCHING_INFO with integer level keys, as build_segmentor converts it
+    (seg3d/utils/config.py:42-67, seg3d/models/builder.py:10-15)."""
+    spec = [[(16, 0, 16), (64, 16, 64), (256, 64, 256), (800, 256, 100000)],
+            [(32, 0, 32), (128, 32, 128), (512, 128, 512), (800, 512, 100000)],
+            [(64, 0, 64), (160, 64, 160), (384, 160, 384), (800, 384, 100000)],
+            [(128, 0, 128), (256, 128, 256), (512, 256, 512), (800, 512, 100000)]]
+    return [{i: {'max_tokens': t, 'batching_range': [lo, hi]} for i, (t, lo, hi) in enumerate(level)} for level in spec]
+
+
+DATASET_CONFIGS = {
+    # configs/waymo_one_sweep.yaml + seg3d/utils/config.py defaults
+    'waymo_one_sweep': dict(voxel_size=[0.1, 0.1, 0.1], point_cloud_range=[-72, -72, -2, 72, 72, 4.4],
+                            use_cylinder=False, use_multi_sweeps=False, num_sweeps=1),
+    # configs/waymo_one_sweep_cylinder.yaml:2-4
+    'waymo_one_sweep_cylinder': dict(voxel_size=[0.05, 0.012, 0.1], point_cloud_range=[0, -3.1415926, -2, 75.2, 3.1415926, 5.2],
+                                     use_cylinder=True, use_multi_sweeps=False, num_sweeps=1),
+    # configs/waymo_multi_sweeps.yaml:2-4
+    'waymo_multi_sweeps': dict(voxel_size=[0.1, 0.1, 0.1], point_cloud_range=[-72, -72, -2, 72, 72, 4.4],
+                               use_cylinder=False, use_multi_sweeps=True, num_sweeps=3),
+}
+
+
+def dataset_spec(name):
+    """The handful of dataset properties Segformer reads (waymo_dataset.py:51-77)."""
+    c = DATASET_CONFIGS[name]
+    vs, pcr, grid = _geometry(c['voxel_size'], c['point_cloud_range'])
+    return SimpleNamespace(name=name, dim_point=6, use_cylinder=c['use_cylinder'], use_multi_sweeps=c['use_multi_sweeps'],
+                           num_sweeps=c['num_sweeps'], use_image_feature=False, dim_image_feature=28, num_classes=22,
+                           grid_size=grid, voxel_size=vs, point_cloud_range=pcr)
+
+
+def build_segformer(config='waymo_one_sweep', compute_dtype=torch.float32, depths=(3, 4, 8, 3), window_shape=(10, 10, 8),
+                    drop_path_rate=0.3, batching_info=None, seed=0):
+    """build_segmentor for MODEL.SEGMENTOR == 'segformer' (builder.py:8-17) with random-init weights."""
+    torch.manual_seed(seed)
+    ds = dataset_spec(config)
+    return Segformer(ds, batching_info or default_batching_info(), list(window_shape), list(depths), drop_path_rate,
+                     compute_dtype=compute_dtype)

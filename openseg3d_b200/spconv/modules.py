@@ -1,0 +1,219 @@
+"""SubMConv3d / SparseConv3d / SparseInverseConv3d / SparseSequential over libos3d (stage 3).
+
+Parameter names and layouts follow spconv 2.x so reference checkpoints load unchanged: ``weight``
+[Cout, kz, ky, kx, Cin], optional ``bias`` [Cout].
+"""
+import math
+
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from .. import _lib
+from .rulebook import build_strided_rulebook, build_subm_rulebook
+from .tensor import SparseConvTensor
+
+
+class SparseModule(nn.Module):
+    """Marker base class: SparseSequential hands these the SparseConvTensor, everything else the features."""
+    pass
+
+
+def _triple(v):
+    return tuple(v) if isinstance(v, (list, tuple)) else (v, v, v)
+
+
+def sparse_conv_forward(features, nbr, weight, bias, packed_cache, scale=None, shift=None, residual=None, relu=False):
+    """out[r] = epilogue( sum_k features[nbr[r, k]] @ W[:, k, :].T ).
+
+    fp32 features -> exact FP32-pipe kernel (+ torch epilogue); bf16 features -> tcgen05 kernel with the epilogue
+    (scale/shift = folded bias + BatchNorm, residual, ReLU) fused."""
+    _lib.require_cuda(features, nbr)
+    features = features.contiguous()
+    m_out, cout, cin = nbr.shape[0], weight.shape[0], weight.shape[-1]
+    if features.shape[1] != cin:
+        raise RuntimeError(f'sparse conv: features have {features.shape[1]} channels, weight expects {cin}')
+    if features.dtype == torch.float32:
+        w = packed_cache.get('f32', weight)
+        out = torch.empty((m_out, cout), dtype=torch.float32, device=features.device)
+        _lib.call('os3d_spconv_fwd_f32', features, nbr, m_out, cin, cout, w, bias if scale is None else None, out)
+        if scale is not None:
+            out = out * scale + shift
+        if residual is not None:
+            out = out + residual
+        return F.relu_(out) if relu else out
+    if features.dtype == torch.bfloat16:
+        w, cin_pad = packed_cache.get('bf16', weight)
+        if cin_pad != cin:
+            features = F.pad(features, (0, cin_pad - cin))
+        if scale is None and bias is not None:
+            scale, shift = torch.ones_like(bias, dtype=torch.float32), bias.float()
+        out = torch.empty((m_out, cout), dtype=torch.bfloat16, device=features.device)
+        _lib.call('os3d_spconv_fwd_bf16', features, nbr, m_out, cin_pad, cout, w, scale, shift,
+                  residual.contiguous() if residual is not None else None, int(relu), out)
+        return out
+    raise RuntimeError(f'sparse conv: unsupported feature dtype {features.dtype}')
+
+
+class _PackedWeights(object):
+    """Kernel-layout copies of a conv weight, rebuilt when the parameter changes (version counter / storage)."""
+
+    def __init__(self):
+        self._store = {}
+
+    def get(self, kind, weight):
+        tag = (weight.data_ptr(), weight._version, weight.device)
+        hit = self._store.get(kind)
+        if hit is not None and hit[0] == tag:
+            return hit[1]
+        cout, cin = weight.shape[0], weight.shape[-1]
+        w32 = weight.detach().float().contiguous()
+        if kind == 'f32':
+            packed = torch.empty((27, cin, cout), dtype=torch.float32, device=weight.device)
+            _lib.call('os3d_pack_weight_f32', w32, cin, cout, packed)
+            val = packed
+        else:
+            cin_pad = (cin + 7) // 8 * 8
+            import ctypes
+            elems = ctypes.c_int64(0)
+            _lib.lib().os3d_spconv_bf16_packed_elems(cin_pad, cout, ctypes.byref(elems))
+            packed = torch.empty(elems.value, dtype=torch.bfloat16, device=weight.device)
+            _lib.call('os3d_pack_weight_bf16', w32, cin, cout, cin_pad, packed)
+            val = (packed, cin_pad)
+        self._store[kind] = (tag, val)
+        return val
+
+
+class _SparseConvBase(SparseModule):
+    def __init__(self, in_channels, out_channels, kernel_size, stride, padding, dilation, bias, indice_key):
+        super().__init__()
+        if _triple(kernel_size) != (3, 3, 3) or _triple(dilation) != (1, 1, 1):
+            raise NotImplementedError('openseg3d_b200.spconv implements 3x3x3 kernels with dilation 1 (all the reference uses)')
+        self.in_channels, self.out_channels = in_channels, out_channels
+        self.kernel_size, self.stride, self.padding, self.dilation = _triple(kernel_size), _triple(stride), _triple(padding), (1, 1, 1)
+        self.indice_key = indice_key
+        self.weight = nn.Parameter(torch.empty(out_channels, 3, 3, 3, in_channels))
+        self.bias = nn.Parameter(torch.empty(out_channels)) if bias else None
+        self._packed = _PackedWeights()
+        self.reset_parameters()
+
+    def reset_parameters(self):
+        # same scheme torch / spconv use for conv layers: kaiming_uniform(a=sqrt(5)) over fan_in = 27 * Cin
+        fan_in = 27 * self.in_channels
+        bound = math.sqrt(6.0 / ((1 + 5) * fan_in))
+        nn.init.uniform_(self.weight, -bound, bound)
+        if self.bias is not None:
+            nn.init.uniform_(self.bias, -1 / math.sqrt(fan_in), 1 / math.sqrt(fan_in))
+
+    def extra_repr(self):
+        return (f'{self.in_channels}, {self.out_channels}, kernel_size={self.kernel_size}, stride={self.stride}, '
+                f'padding={self.padding}, bias={self.bias is not None}, indice_key={self.indice_key}')
+
+    def _check_grad(self, x):
+        if torch.is_grad_enabled() and (x.features.requires_grad or self.weight.requires_grad):
+            raise NotImplementedError('sparse conv backward is not built yet (DESIGN.md, "Not yet built"); '
+                                      'run the forward under torch.no_grad()')
+
+    # subclasses: table(x) -> (nbr, out SparseConvTensor prototype)
+    def forward(self, x, scale=None, shift=None, residual=None, relu=False):
+        self._check_grad(x)
+        nbr, out_proto = self._table(x)
+        feats = sparse_conv_forward(x.features, nbr, self.weight, self.bias, self._packed, scale, shift, residual, relu)
+        return out_proto(feats)
+
+
+class SubMConv3d(_SparseConvBase):
+    def __init__(self, in_channels, out_channels, kernel_size, stride=1, padding=0, dilation=1, groups=1, bias=True,
+                 indice_key=None, algo=None):
+        super().__init__(in_channels, out_channels, kernel_size, 1, 1, dilation, bias, indice_key)
+
+    def _table(self, x):
+        rb = x.find_indice_pair(self.indice_key)
+        if rb is None or rb.kind != 'subm' or rb.indices is not x.indices:
+            rb = build_subm_rulebook(x)
+            if self.indice_key is not None:
+                x.indice_dict[self.indice_key] = rb
+        return rb.nbr, x.replace_feature
+
+
+class SparseConv3d(_SparseConvBase):
+    def __init__(self, in_channels, out_channels, kernel_size, stride=1, padding=0, dilation=1, groups=1, bias=True,
+                 indice_key=None, algo=None):
+        if _triple(stride) != (2, 2, 2) or _triple(padding) != (1, 1, 1):
+            raise NotImplementedError('SparseConv3d: kernel 3 / stride 2 / padding 1 only (all the reference uses)')
+        super().__init__(in_channels, out_channels, kernel_size, stride, padding, dilation, bias, indice_key)
+
+    def _table(self, x):
+        rb = x.find_indice_pair(self.indice_key)
+        if rb is None or rb.kind != 'strided' or rb.in_indices is not x.indices:
+            rb = build_strided_rulebook(x)
+            if self.indice_key is not None:
+                x.indice_dict[self.indice_key] = rb
+        return rb.fwd_nbr, lambda f: SparseConvTensor(f, rb.out_indices, rb.out_shape, x.batch_size, x.indice_dict,
+                                                      x._site_table)
+
+
+class SparseInverseConv3d(_SparseConvBase):
+    def __init__(self, in_channels, out_channels, kernel_size, indice_key=None, bias=True, algo=None):
+        super().__init__(in_channels, out_channels, kernel_size, 1, 0, 1, bias, indice_key)
+
+    def _table(self, x):
+        rb = x.find_indice_pair(self.indice_key)
+        if rb is None or rb.kind != 'strided':
+            raise RuntimeError(f'SparseInverseConv3d needs the rulebook of an earlier SparseConv3d with indice_key={self.indice_key}')
+        if rb.out_indices.shape[0] != x.features.shape[0]:
+            raise RuntimeError('SparseInverseConv3d input does not live on the sites that SparseConv3d produced')
+        return rb.inv_nbr, lambda f: SparseConvTensor(f, rb.in_indices, rb.in_shape, x.batch_size, x.indice_dict,
+                                                      x._site_table)
+
+
+def bn_scale_shift(bn, conv_bias=None):
+    """Eval-mode BatchNorm1d (and the conv bias before it) as y = acc * scale + shift, in fp32."""
+    inv = torch.rsqrt(bn.running_var.float() + bn.eps)
+    scale = inv * bn.weight.float() if bn.affine else inv
+    shift = -bn.running_mean.float() * scale
+    if bn.affine:
+        shift = shift + bn.bias.float()
+    if conv_bias is not None:
+        shift = shift + conv_bias.float() * scale
+    return scale.contiguous(), shift.contiguous()
+
+
+class SparseSequential(SparseModule):
+    """Applies SparseModules to the SparseConvTensor and plain nn.Modules to its ``.features``.
+
+    At inference a (conv, BatchNorm1d, ReLU) run is executed as ONE kernel: BatchNorm folds into a per-channel
+    scale/shift applied in the conv epilogue together with the ReLU."""
+
+    def __init__(self, *args):
+        super().__init__()
+        for i, m in enumerate(args):
+            self.add_module(str(i), m)
+
+    def __getitem__(self, i):
+        return list(self._modules.values())[i]
+
+    def __len__(self):
+        return len(self._modules)
+
+    def forward(self, x):
+        mods = list(self._modules.values())
+        i = 0
+        while i < len(mods):
+            m = mods[i]
+            if isinstance(m, _SparseConvBase) and not self.training and i + 1 < len(mods) \
+                    and isinstance(mods[i + 1], nn.BatchNorm1d) and isinstance(x, SparseConvTensor):
+                relu = i + 2 < len(mods) and isinstance(mods[i + 2], nn.ReLU)
+                scale, shift = bn_scale_shift(mods[i + 1], m.bias)
+                x = m(x, scale=scale, shift=shift, relu=relu)
+                i += 3 if relu else 2
+                continue
+            if isinstance(m, SparseModule):
+                x = m(x)
+            elif isinstance(x, SparseConvTensor):
+                if x.features.shape[0] > 0:
+                    x = x.replace_feature(m(x.features))
+            else:
+                x = m(x)
+            i += 1
+        return x

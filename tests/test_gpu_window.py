@@ -1,0 +1,118 @@
+"""GPU parity, stage 4 against the REFERENCE's own outputs (tests/golden/swformer_block.npz, produced by
+seg3d/models/layers/point_transformer_layer.py + cosine_msa.py + swformer_utils.py): integer partition outputs
+bit-exact, position embedding / attention / SWFormer block within fp32 rel 1e-4 (bf16: rel 2e-2)."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope='module')
+def g(golden_dir):
+    return np.load(os.path.join(golden_dir, 'swformer_block.npz'))
+
+
+def _binfo(g):
+    return {int(r[0]): {'max_tokens': int(r[1]), 'batching_range': (int(r[2]), int(r[3]))} for r in g['levels']}
+
+
+def _layer_and_info(g, dtype=torch.float32):
+    from openseg3d_b200 import spconv
+    from openseg3d_b200.models import SparseWindowPartitionLayer
+    layer = SparseWindowPartitionLayer(_binfo(g), tuple(g['window'].tolist()), tuple(g['sparse_xyz'].tolist()))
+    sx, sy, sz = g['sparse_xyz'].tolist()
+    x = spconv.SparseConvTensor(torch.from_numpy(g['feats']).cuda().to(dtype), torch.from_numpy(g['coords']).cuda(),
+                                [sz, sy, sx], 2)
+    return layer, layer(x)
+
+
+def test_partition_bit_exact_vs_reference(g):
+    from openseg3d_b200.models.layers import flat2window
+    layer, info = _layer_and_info(g)
+    binfo = _binfo(g)
+    for s in range(2):
+        assert np.array_equal(info[f'batch_win_inds_shift{s}'].cpu().numpy(), g[f'win_s{s}'])
+        assert np.array_equal(info[f'coors_in_win_shift{s}'].cpu().numpy(), g[f'inwin_s{s}'])
+        assert np.array_equal(info[f'voxel_batching_level_shift{s}'].cpu().numpy(), g[f'lvl_s{s}'])
+        inds = info[f'flat2win_inds_shift{s}'].materialize()
+        seg = inds['segments']
+        li = seg.check_no_drop()
+        levels = [bl for bl in binfo if f'slot_s{s}_l{bl}' in g]
+        assert sorted(inds.levels()) == sorted(levels)
+        for bl in levels:
+            assert np.array_equal(inds[bl][0].cpu().numpy(), g[f'slot_s{s}_l{bl}'])
+            assert np.array_equal(inds[bl][1][0].cpu().numpy(), g[f'where_s{s}_l{bl}'])
+        # segment table: level-major, covers every voxel once, windows ascending inside a level
+        n_win = int(li[13])
+        order = seg.order.cpu().numpy()
+        assert np.array_equal(np.sort(order), np.arange(order.shape[0]))
+        start, length = seg.seg_start.cpu().numpy()[:n_win], seg.seg_len.cpu().numpy()[:n_win]
+        win = g[f'win_s{s}']
+        for r in range(n_win):
+            rows = order[start[r]:start[r] + length[r]]
+            assert len(set(win[rows].tolist())) == 1 and (np.diff(rows) > 0).all()
+    # padded position embedding of shift 1 against the reference's padded tensors
+    pos3 = flat2window(info['pos_dict_shift1']['flat'], info['flat2win_inds_shift1'])
+    for bl, v in pos3.items():
+        np.testing.assert_allclose(v.cpu().numpy(), g[f'pos_s1_l{bl}'], rtol=0, atol=2e-6)
+    # implicit key masks: padded slots are exactly the ones no voxel maps to
+    ones = torch.ones(g['coords'].shape[0], 1, device='cuda')
+    for bl, v in flat2window(ones, info['flat2win_inds_shift0']).items():
+        assert np.array_equal((v.squeeze(2) == 0).cpu().numpy(), g[f'mask_s0_l{bl}'])
+
+
+def _block(g, dtype=torch.float32):
+    from openseg3d_b200.models import SWFormerBlock
+    blk = SWFormerBlock(g['feats'].shape[1], int(g['heads']), depth=int(g['depth']), drop_path=0.0)
+    sd = {k[3:]: torch.from_numpy(g[k]) for k in g.files if k.startswith('sd.')}
+    missing, unexpected = blk.load_state_dict(sd, strict=True)         # reference state_dict keys load unchanged
+    return blk.cuda().eval()
+
+
+def test_attention_and_block_fp32_vs_reference(g):
+    layer, info = _layer_and_info(g)
+    blk = _block(g)
+    with torch.no_grad():
+        attn = blk.layers[0].win_attn(info['voxel_features'], info['pos_dict_shift0'], info['flat2win_inds_shift0'],
+                                      info['key_mask_shift0'])
+        out = blk(info)
+    np.testing.assert_allclose(attn.cpu().numpy(), g['attn0'], rtol=1e-4, atol=2e-5)
+    np.testing.assert_allclose(out.cpu().numpy(), g['out'], rtol=1e-4, atol=5e-5)
+
+
+def test_block_bf16_vs_reference(g):
+    layer, info = _layer_and_info(g, torch.bfloat16)
+    blk = _block(g)
+    with torch.no_grad():
+        out = blk(info).float().cpu().numpy()
+    ref = g['out']
+    err = np.abs(out - ref) / (np.abs(ref) + 1.0)
+    assert err.max() < 6e-2 and err.mean() < 1e-2, (err.max(), err.mean())
+
+
+def test_get_inner_win_inds_stable_rank():
+    from openseg3d_b200.ops import get_inner_win_inds
+    from oracle import oracle
+    torch.manual_seed(0)
+    grp = torch.randint(0, 500, (20000,))
+    grp[:3000] = 7                                     # one group longer than the in-kernel staging buffer
+    out = get_inner_win_inds(grp.cuda())
+    assert out.dtype == grp.dtype
+    assert np.array_equal(out.cpu().numpy(), oracle.ingroup_rank(grp.numpy()))
+
+
+def test_partition_empty_and_single():
+    from openseg3d_b200 import spconv
+    from openseg3d_b200.models import SparseWindowPartitionLayer, SWFormerBlock
+    binfo = {0: {'max_tokens': 16, 'batching_range': (0, 16)}, 1: {'max_tokens': 800, 'batching_range': (16, 100000)}}
+    layer = SparseWindowPartitionLayer(binfo, (10, 10, 8), (100, 100, 16))
+    x = spconv.SparseConvTensor(torch.randn(1, 48).cuda(), torch.tensor([[0, 3, 4, 5]], dtype=torch.int32).cuda(),
+                                [16, 100, 100], 1)
+    info = layer(x)
+    blk = SWFormerBlock(48, 8, depth=2).cuda().eval()
+    with torch.no_grad():
+        out = blk(info)
+    assert out.shape == (1, 48) and bool(torch.isfinite(out).all())
