@@ -1,0 +1,251 @@
+#!/usr/bin/env python
+"""bench.py -- points/sec of the OpenSeg3D voxel-backbone hot path (Segformer forward) on B200.
+
+  python bench.py --gpus N --steps K --warmup W            (N > 1: launched under torchrun, one rank per GPU)
+  python bench.py --impl reference ...                      (the CPU oracle on the host cores, same metric)
+
+Workload (BASELINE.json configs[1]): configs/waymo_one_sweep.yaml inference, a batch of 8 synthetic Waymo-shape
+frames per GPU (~181k points each), random-init Segformer (PointTransformer backbone), bf16 backbone.
+A step = voxelize -> point MLP -> scatter-max -> sparse UNet with window attention -> gather -> point head.
+Frames are sharded over ranks (weak scaling, no data-path collective: inference has none).
+
+JSON line keys follow the driver contract; `value` has the points already in HBM, `e2e` starts from pinned host
+memory and ends with the predicted labels back on the host.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+FRAMES_PER_GPU = 8
+CONFIG = 'waymo_one_sweep'
+CPU_SAMPLE_COLS = 662          # 1/4 of the 2650 azimuth columns of one frame -> ~45k points, ~10-30 s of CPU work
+
+
+def peaks():
+    path = os.path.join(ROOT, 'MEASURED_PEAKS.json')
+    if os.path.exists(path):
+        p = json.load(open(path))
+        return dict(hbm=p['hbm_gbs'], tensor=p.get('bf16_tflops_sustained', p['bf16_tflops']), src='measured')
+    return dict(hbm=6650.0, tensor=1400.0, src='fallback')
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    Q = ('clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,'
+         'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap')
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.rows, self.stop_flag = index, [], False
+
+    def run(self):
+        while not self.stop_flag:
+            try:
+                out = subprocess.run(['nvidia-smi', '-i', str(self.index), f'--query-gpu={self.Q}',
+                                      '--format=csv,noheader,nounits'], capture_output=True, text=True, timeout=5).stdout
+                f = [x.strip() for x in out.strip().split(',')]
+                if len(f) == 6:
+                    self.rows.append(f)
+            except Exception:
+                pass
+            time.sleep(0.1)
+
+    def summary(self):
+        if not self.rows:
+            return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['nvidia-smi unavailable']}
+        sm = sorted(float(r[0]) for r in self.rows)
+        names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
+        reasons = [n for i, n in enumerate(names) if any(r[2 + i] == 'Active' for r in self.rows)]
+        return {'sm_mhz': sm[len(sm) // 2], 'sm_max_mhz': float(self.rows[0][1]), 'reasons': reasons,
+                'samples': len(self.rows)}
+
+
+def cpu_forward_sample(threads):
+    """The oracle's forward (the CPU restatement of the reference path) on one quarter-sweep frame.  Returns
+    (points_per_sec, n_points, seconds)."""
+    import torch
+    from openseg3d_b200 import synthetic
+    from openseg3d_b200.models import build_segformer
+    from openseg3d_b200.models.segmentors import default_batching_info, DATASET_CONFIGS
+    from oracle import oracle
+    torch.set_num_threads(threads)
+    model = build_segformer(CONFIG).eval()
+    sd = model.state_dict()
+    pts, _ = synthetic.make_batch([0], 1, False, synthetic.N_BEAMS, CPU_SAMPLE_COLS)
+    c = DATASET_CONFIGS[CONFIG]
+    t0 = time.perf_counter()
+    with torch.no_grad():
+        oracle.segformer_forward(sd, pts, c['voxel_size'], c['point_cloud_range'], default_batching_info(), [10, 10, 8],
+                                 [3, 4, 8, 3])
+    dt = time.perf_counter() - t0
+    return pts.shape[0] / dt, pts.shape[0], dt
+
+
+def run_reference(args):
+    """--impl reference: the reference's own CPU implementation of the path is not runnable (spconv / torch_scatter
+    absent, GPU-only extensions), so this times the oracle port on the host cores -- DESIGN.md "Measurement"."""
+    rank = int(os.environ.get('RANK', '0'))
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    from oracle import oracle
+    oracle.lib()
+    vals = []
+    for i in range(args.warmup + args.steps):
+        pps, n, dt = cpu_forward_sample(cores)
+        if i >= args.warmup:
+            vals.append((pps, dt))
+    pps = sum(v[0] for v in vals) / len(vals)
+    ms = 1e3 * sum(v[1] for v in vals) / len(vals)
+    sample = f'1 frame x {CPU_SAMPLE_COLS}/2650 azimuth columns ({n} points) per step, fp32, oracle port'
+    line = {'impl': 'reference', 'metric': 'points/sec, Waymo 1-sweep seg forward', 'value': pps, 'unit': 'points/s',
+            'n_gpus': args.gpus, 'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': ms, 'higher_is_better': True,
+            'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
+            'config': {'workload': f'{CONFIG} forward, oracle CPU port, {sample}'},
+            'cpu_baseline': {'value': pps, 'unit': 'points/s', 'cores': cores, 'kind': 'port', 'sample': sample},
+            'e2e': {'value': pps, 'unit': 'points/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
+            'gpu_launches': 0}
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=10)
+    ap.add_argument('--warmup', type=int, default=3)
+    ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
+    ap.add_argument('--dtype', default='bf16', choices=['bf16', 'f32'])
+    ap.add_argument('--frames', type=int, default=FRAMES_PER_GPU)
+    ap.add_argument('--no-cpu-baseline', action='store_true')
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == 'ours' else args.warmup
+    if args.impl == 'reference':
+        return run_reference(args)
+
+    import torch
+    import torch.distributed as dist
+    from openseg3d_b200 import _lib, synthetic
+    from openseg3d_b200.models import build_segformer
+    from openseg3d_b200.spconv import modules as spmod
+    from openseg3d_b200.models import layers as lay
+
+    rank, world = int(os.environ.get('RANK', '0')), int(os.environ.get('WORLD_SIZE', '1'))
+    local = int(os.environ.get('LOCAL_RANK', '0'))
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group('nccl', device_id=torch.device('cuda', local))
+    _lib.lib()                                    # fail loudly if the CUDA library is missing
+    dtype = torch.bfloat16 if args.dtype == 'bf16' else torch.float32
+    model = build_segformer(CONFIG, compute_dtype=dtype).cuda().eval()
+
+    seeds = [rank * args.frames + i for i in range(args.frames)]
+    pts_np, _ = synthetic.make_batch(seeds, 1, False)
+    n_points = pts_np.shape[0]
+    host = torch.from_numpy(pts_np).pin_memory()
+    dev_pts = host.cuda(non_blocking=True)
+    labels_host = torch.empty(n_points, dtype=torch.uint8).pin_memory()
+
+    def step_resident():
+        with torch.no_grad():
+            return model({'points': dev_pts, 'batch_size': args.frames})['point_out']
+
+    def step_e2e():
+        with torch.no_grad():
+            d = host.cuda(non_blocking=True)
+            out = model({'points': d, 'batch_size': args.frames})['point_out']
+            labels_host.copy_(out.argmax(dim=1).to(torch.uint8), non_blocking=True)   # tools/test.py:56 argmax + .cpu()
+        torch.cuda.current_stream().synchronize()
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], device='cuda')
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms.item())
+
+    for _ in range(args.warmup):
+        step_resident()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    l0 = _lib.launches()
+    total_ms = timed(step_resident, args.steps)
+    launches = _lib.launches() - l0
+    sampler.stop_flag = True
+    step_e2e()
+    e2e_ms = timed(step_e2e, args.steps)
+
+    tot_pts = torch.tensor([float(n_points)], device='cuda')
+    if world > 1:
+        dist.all_reduce(tot_pts)
+    total_points = float(tot_pts.item())
+    value = total_points * args.steps / (total_ms * 1e-3)
+    e2e_value = total_points * args.steps / (e2e_ms * 1e-3)
+
+    # ---- per-kernel timing of one more step (CUDA events on the launching stream) for the roofline ----
+    prof = []
+    _lib.PROFILE = prof
+    step_resident()
+    torch.cuda.synchronize()
+    _lib.PROFILE = None
+    by = {}
+    for name, e0, e1, work in prof:
+        d = by.setdefault(name, [0.0, 0.0, 0])
+        d[0] += e0.elapsed_time(e1)
+        d[1] += work
+        d[2] += 1
+    pk = peaks()
+    conv_ms, conv_flops, conv_n = by.get('os3d_spconv_fwd_bf16', by.get('os3d_spconv_fwd_f32', [0.0, 0.0, 0]))
+    achieved = conv_flops / (conv_ms * 1e-3) / 1e12 if conv_ms else 0.0
+    roofline = {'kernel': 'spconv_tc_kernel (tcgen05 sparse conv, 19 launches/step)' if dtype == torch.bfloat16
+                else 'spconv_f32_kernel', 'bound': 'tensor', 'achieved': achieved, 'peak': pk['tensor'],
+                'unit': 'TFLOP/s', 'frac': achieved / pk['tensor'], 'traffic': None, 'peak_source': pk['src'],
+                'launches_per_step': conv_n, 'ms_per_step': conv_ms, 'share_of_step': conv_ms / (total_ms / args.steps),
+                'algorithmic_gflop_per_step': conv_flops / 1e9,
+                'other_kernels_ms_per_step': {k: round(v[0], 3) for k, v in sorted(by.items()) if 'spconv_fwd' not in k}}
+
+    line = {'metric': 'points/sec, Waymo 1-sweep seg forward', 'value': value, 'unit': 'points/s', 'n_gpus': world,
+            'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': total_ms / args.steps, 'higher_is_better': True,
+            'scaling': 'weak', 'vs_baseline': None, 'dtype': args.dtype, 'data': 'synthetic',
+            'config': {'workload': f'configs/{CONFIG}.yaml inference, batch of {args.frames} synthetic frames per GPU '
+                                   f'({n_points} points/GPU), voxelize + sparse UNet + window attention, random-init',
+                       'frames_per_gpu': args.frames, 'points_per_gpu': n_points, 'parallelism': f'frames sharded x{world}',
+                       'l2': 'per-step working set (activations > 2 GB) >> 126 MB L2; no explicit flush'},
+            'e2e': {'value': e2e_value, 'unit': 'points/s', 'h2d_bytes_per_step': host.numel() * 4 * world,
+                    'd2h_bytes_per_step': n_points * world, 'ms_per_step': e2e_ms / args.steps},
+            'gpu_launches': launches, 'roofline': roofline}
+    if rank == 0:
+        sampler.join(timeout=2)
+        line['clocks'] = sampler.summary()
+        if world == 1 and not args.no_cpu_baseline:
+            cores = os.cpu_count() or 1
+            pps, n, dt = cpu_forward_sample(cores)
+            line['cpu_baseline'] = {'value': pps, 'unit': 'points/s', 'cores': cores, 'kind': 'port',
+                                    'sample': f'1 frame x {CPU_SAMPLE_COLS}/2650 azimuth columns ({n} points), fp32 oracle '
+                                              f'forward, {dt:.1f} s'}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == '__main__':
+    main()

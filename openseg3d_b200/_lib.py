@@ -90,21 +90,39 @@ def stream():
     return torch.cuda.current_stream().cuda_stream
 
 
+# CUDA kernels launched by each entry point (memsets not counted) -- bench.py's gpu_launches evidence
+KERNELS_PER_CALL = {
+    'os3d_voxelize': 5, 'os3d_cart2polar_rows': 1, 'os3d_scatter_max_f32': 2, 'os3d_scatter_mean_f32': 2,
+    'os3d_scatter_max_bwd_f32': 1, 'os3d_scatter_mean_bwd_f32': 1, 'os3d_gather_rows': 1, 'os3d_scatter_add_rows_f32': 1,
+    'os3d_hash_build': 1, 'os3d_subm_table': 1, 'os3d_strided_sites': 4, 'os3d_strided_tables': 2,
+    'os3d_spconv_fwd_f32': 1, 'os3d_spconv_fwd_bf16': 1, 'os3d_pack_weight_f32': 1, 'os3d_pack_weight_bf16': 1,
+    'os3d_window_partition': 7, 'os3d_group_partition': 7, 'os3d_pos_embed': 1, 'os3d_qk_normalize': 1,
+    'os3d_window_attention': 1,
+}
 _launches = 0
+PROFILE = None      # bench.py sets this to a list to collect (name, start_event, end_event, work) per call
 
 
 def launches():
-    """Number of libos3d entry-point calls so far (bench.py reports it as its kernel-launch evidence)."""
+    """Number of libos3d CUDA kernels launched so far (bench.py reports the delta over its timed region)."""
     return _launches
 
 
-def call(name, *args):
-    """Invoke an entry point on torch's current stream; raise RuntimeError on a non-zero status."""
+def call(name, *args, work=None):
+    """Invoke an entry point on torch's current stream; raise RuntimeError on a non-zero status.
+    ``work``: optional callable returning the algorithmic FLOPs / bytes of this call (evaluated only when profiling)."""
     global _launches
     L = lib()
     conv = [ptr(a) if isinstance(a, torch.Tensor) else a for a in args]
+    prof = PROFILE
+    if prof is not None:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
     rc = getattr(L, name)(*conv, stream())
-    _launches += 1
+    if prof is not None:
+        e1.record()
+        prof.append((name, e0, e1, float(work()) if work is not None else 0.0))
+    _launches += KERNELS_PER_CALL.get(name, 1)
     if rc != 0:
         raise RuntimeError(f'{name} failed: {L.os3d_error_string(rc).decode()} (code {rc})')
 

@@ -36,7 +36,8 @@ def sparse_conv_forward(features, nbr, weight, bias, packed_cache, scale=None, s
     if features.dtype == torch.float32:
         w = packed_cache.get('f32', weight)
         out = torch.empty((m_out, cout), dtype=torch.float32, device=features.device)
-        _lib.call('os3d_spconv_fwd_f32', features, nbr, m_out, cin, cout, w, bias if scale is None else None, out)
+        _lib.call('os3d_spconv_fwd_f32', features, nbr, m_out, cin, cout, w, bias if scale is None else None, out,
+                  work=lambda: 2.0 * cin * cout * int((nbr >= 0).sum().item()))
         if scale is not None:
             out = out * scale + shift
         if residual is not None:
@@ -50,7 +51,8 @@ def sparse_conv_forward(features, nbr, weight, bias, packed_cache, scale=None, s
             scale, shift = torch.ones_like(bias, dtype=torch.float32), bias.float()
         out = torch.empty((m_out, cout), dtype=torch.bfloat16, device=features.device)
         _lib.call('os3d_spconv_fwd_bf16', features, nbr, m_out, cin_pad, cout, w, scale, shift,
-                  residual.contiguous() if residual is not None else None, int(relu), out)
+                  residual.contiguous() if residual is not None else None, int(relu), out,
+                  work=lambda: 2.0 * cin * cout * int((nbr >= 0).sum().item()))
         return out
     raise RuntimeError(f'sparse conv: unsupported feature dtype {features.dtype}')
 
