@@ -153,21 +153,22 @@ typedef struct {
  *   atomicAdd rank is a race, this is its deterministic member).  flat2window slot = win_rank * max_tokens + inner.
  * Segment outputs: order [m] int32 = voxel rows grouped by window (ascending window id, ascending row inside);
  *   seg_start / seg_len [<= m + 1] int32: one entry per non-empty window, level-major (all level-0 windows first),
- *   ascending window id inside a level;
+ *   ascending window id inside a level;  pos_seg [m, 2] int32: (start, length) in `order` of the window that owns
+ *   each grouped position (what the tensor-core attention walks);
  *   level_info: device int32[16] = { n_windows[4], first_window[4], 0,0,0,0, tokens_outside_ranges, n_windows_total,
  *   n_tokens_assigned, tokens_over_capacity }.  (The reference drops over-capacity tokens and then cannot continue
  *   -- SURVEY.md Appendix C; callers treat a non-zero count as an error.) */
 int os3d_window_partition(const int32_t *idx, int64_t m, int batch, const os3d_window_cfg_t *cfg, int32_t *win_count,
                           int32_t *win_meta, int32_t *block_sums, int64_t n_blocks, int64_t *win_id, int32_t *in_win,
                           int32_t *level, int32_t *win_rank, int32_t *inner, int32_t *order, int32_t *seg_start,
-                          int32_t *seg_len, int32_t *level_info, void *stream);
+                          int32_t *seg_len, int32_t *pos_seg, int32_t *level_info, void *stream);
 
 /* The same partition over caller-supplied group ids in [0, n_groups) (cfg supplies only the batching levels).
  * replaces: get_inner_win_inds as a stand-alone op (seg3d/ops/ingroup_inds/ingroup_inds.py:7-20): `inner` is the rank. */
 int os3d_group_partition(const int64_t *group, int64_t n, int64_t n_groups, const os3d_window_cfg_t *cfg, int32_t *count,
                          int32_t *meta, int32_t *block_sums, int64_t n_blocks, int32_t *level, int32_t *group_rank,
-                         int32_t *inner, int32_t *order, int32_t *seg_start, int32_t *seg_len, int32_t *level_info,
-                         void *stream);
+                         int32_t *inner, int32_t *order, int32_t *seg_start, int32_t *seg_len, int32_t *pos_seg,
+                         int32_t *level_info, void *stream);
 
 /* Sinusoidal window position embedding, flat [m, c] (f32 or bf16 by elem_size).
  * replaces: SparseWindowPartitionLayer.get_pos_embed (point_transformer_layer.py:152-207). */
@@ -189,6 +190,20 @@ int os3d_window_attention(const void *q, const void *k, const void *v, int64_t l
                           const int32_t *order, const int32_t *seg_start, const int32_t *seg_len,
                           const int32_t *level_info, const int *lvl_tokens, const float *tau, float tau_min,
                           int elem_size, void *out, void *stream);
+
+/* The same attention on the tcgen05 tensor cores (bf16): QK^T and PV as UMMA tiles with TMEM accumulators, q / k
+ * normalisation folded into the gather (do NOT call os3d_qk_normalize first).  Head-padded layout: head h occupies
+ * columns [h*dp, (h+1)*dp) of q / k / v / out rows with dp = head_dim rounded up to 16 (16, 32 or 48; pad columns
+ * zero -- the Python layer pads the projection weights).  pos_seg from os3d_window_partition. */
+int os3d_window_attention_bf16_tc(const void *q, const void *k, const void *v, int64_t ld, int64_t ldv, int64_t m,
+                                  int heads, int dp, const int32_t *order, const int32_t *pos_seg,
+                                  const int32_t *level_info, const float *tau, float tau_min, void *out, int64_t ldo,
+                                  void *stream);
+
+/* out = resid + LayerNorm(x) * w + b over rows of c elements (c % 8 == 0); resid may be NULL; w, b f32.
+ * replaces: norm1 / norm2 + the residual adds of EncoderLayer.forward (point_transformer_layer.py:288-298). */
+int os3d_layernorm_residual(const void *x, const void *resid, const float *w, const float *b, int64_t m, int c,
+                            float eps, int elem_size, void *out, void *stream);
 
 #ifdef __cplusplus
 }

@@ -1,0 +1,347 @@
+// attention_tc.cu -- stage 4 on the tensor cores: variable-length cosine window attention with tcgen05 / TMEM (bf16).
+//
+// Work item = (128 consecutive tokens of the window-grouped order, one head).  Because `order` groups voxels by
+// window, the keys such a query tile can see are one contiguous range of `order` (from the start of the first touched
+// window to the end of the last), walked in blocks of 64 keys:
+//
+//   gather  : q / k / v head slices (head-padded layout: dp = d rounded up to 16, so a slice is whole UMMA K-steps)
+//             -> shared memory in the K-major no-swizzle core-matrix layout.  q and k are L2-normalised on the way
+//             (F.normalize, cosine_msa.py:152-153) -- the separate normalisation pass disappears; V is transposed.
+//   MMA 1   : S[128 x 64] = Q K^T                  tcgen05.mma kind::f16, accumulator in TMEM columns [0, 64)
+//   softmax : thread t owns query row t (tcgen05.ld 32x32b: lane = row, no shuffles): scale by log2(e)/max(tau,tau_min),
+//             mask keys of other windows (block-diagonal structure: compare window starts), online max / sum,
+//             P = exp2(s - m) as bf16 -> shared memory (A operand of MMA 2); if a row maximum moved, the O accumulator
+//             is rescaled in place in TMEM (tcgen05.ld -> mul -> tcgen05.st).
+//   MMA 2   : O[128 x dp] += P V                   accumulator in TMEM columns [64, 64 + dp)
+//   epilogue: O / l -> bf16 -> out[row, head*dp ...] in the original voxel order.
+//
+// No padding to max_tokens, no [R*h, T, T] score tensor, no key-padding masks (the reference builds all three:
+// swformer_utils.py:34-64, cosine_msa.py:154-176, point_transformer_layer.py:210-220).  128 TMEM columns and ~45 KB
+// of shared memory per CTA -> 4 CTAs per SM overlap each other's gather / MMA / softmax phases.
+#include "common.cuh"
+#include "tc_ptx.cuh"
+
+namespace os3d {
+namespace attn_tc {
+using namespace ptx;
+
+constexpr int kTileQ = 128;
+constexpr int kBlockKeys = 64;
+constexpr int kThreads = 128;
+constexpr int kLbo = 128;                 // bytes between core matrices along K
+constexpr int kTmemCols = 128;            // S: [0, 64), O: [64, 64 + dp)
+
+struct Params {
+  const __nv_bfloat16 *q, *k, *v;         // rows: q, k pitch ld (elements), v pitch ldv; head h at column h * dp
+  int64_t ld, ldv, ldo;
+  const int32_t *order;                   // [n_tokens] voxel row of each grouped position
+  const int2 *pos_seg;                    // [n_tokens] (window start position, window length) of each grouped position
+  const int32_t *level_info;              // [14] = number of grouped positions
+  const float *tau;
+  float tau_min;
+  __nv_bfloat16 *out;
+  int heads;
+};
+
+// smem offset of element chunk (row r, 16-byte K-chunk c) in the K-major no-swizzle layout with 8-row group stride sbo
+__device__ __forceinline__ uint32_t core_off(int r, int c, int sbo) { return (r >> 3) * sbo + c * kLbo + (r & 7) * 16; }
+
+template <int DP>
+__global__ void __launch_bounds__(kThreads) window_attention_tc_kernel(const Params p) {
+  constexpr int kChunks = DP / 8;                         // 16-byte chunks per head slice
+  constexpr int kSboQ = kChunks * kLbo + 16;              // +16: stagger 8-row groups across banks
+  constexpr int kSboP = (kBlockKeys / 8) * kLbo + 16;
+  constexpr int kSboV = (kBlockKeys / 8) * kLbo + 16;     // V^T: rows = head dims, K = keys
+  constexpr int kQBytes = (kTileQ / 8) * kSboQ;
+  constexpr int kKBytes = (kBlockKeys / 8) * kSboQ;
+  constexpr int kVBytes = (DP / 8) * kSboV;
+  constexpr int kPBytes = (kTileQ / 8) * kSboP;
+
+  __shared__ __align__(128) uint8_t q_s[kQBytes];
+  __shared__ __align__(128) uint8_t k_s[kKBytes];
+  __shared__ __align__(128) uint8_t v_s[kVBytes];
+  __shared__ __align__(128) uint8_t p_s[kPBytes];
+  __shared__ int32_t kws_s[kBlockKeys];                   // window start of each key of the block (-1 = no key)
+  __shared__ __align__(8) uint64_t bars[2];
+  __shared__ uint32_t tmem_slot;
+
+  const int tid = threadIdx.x, warp = tid >> 5;
+  const int h = blockIdx.y;
+  const int n_tok = __ldg(p.level_info + 14);
+  const int p0 = blockIdx.x * kTileQ;
+  if (p0 >= n_tok) return;
+  const int p_last = min(p0 + kTileQ, n_tok) - 1;
+
+  const uint32_t bar1 = smem_u32(&bars[0]), bar2 = smem_u32(&bars[1]);
+  if (tid == 0) {
+    mbar_init(bar1, 1);
+    mbar_init(bar2, 1);
+    fence_barrier_init();
+  }
+  if (warp == 0) tmem_alloc(smem_u32(&tmem_slot), kTmemCols);
+
+  // ---- this thread's query row ----
+  const int qp = p0 + tid;
+  const bool q_ok = qp <= p_last;
+  int qws = -2;
+  int32_t qrow = 0;
+  if (q_ok) {
+    qws = __ldg(&p.pos_seg[qp].x);
+    qrow = __ldg(p.order + qp);
+  }
+  {
+    float f[DP];
+    if (q_ok) {
+      const uint4 *src = reinterpret_cast<const uint4 *>(p.q + (int64_t)qrow * p.ld + h * DP);
+      float ss = 0.0f;
+#pragma unroll
+      for (int c = 0; c < kChunks; ++c) {
+        const uint4 u = __ldg(src + c);
+        const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          f[c * 8 + 2 * i] = __uint_as_float(w[i] << 16);
+          f[c * 8 + 2 * i + 1] = __uint_as_float(w[i] & 0xffff0000u);
+          ss = fmaf(f[c * 8 + 2 * i], f[c * 8 + 2 * i], ss);
+          ss = fmaf(f[c * 8 + 2 * i + 1], f[c * 8 + 2 * i + 1], ss);
+        }
+      }
+      const float inv = 1.0f / fmaxf(sqrtf(ss), 1e-12f);
+#pragma unroll
+      for (int i = 0; i < DP; ++i) f[i] *= inv;
+    } else {
+#pragma unroll
+      for (int i = 0; i < DP; ++i) f[i] = 0.0f;
+    }
+#pragma unroll
+    for (int c = 0; c < kChunks; ++c) {
+      uint32_t w[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const __nv_bfloat162 hh = __floats2bfloat162_rn(f[c * 8 + 2 * i], f[c * 8 + 2 * i + 1]);
+        w[i] = *reinterpret_cast<const uint32_t *>(&hh);
+      }
+      *reinterpret_cast<uint4 *>(q_s + core_off(tid, c, kSboQ)) = make_uint4(w[0], w[1], w[2], w[3]);
+    }
+  }
+
+  // key range of the tile: start of the first touched window .. end of the last touched window
+  const int2 seg_first = __ldg(&p.pos_seg[p0]);
+  const int2 seg_last = __ldg(&p.pos_seg[p_last]);
+  const int ks = seg_first.x, ke = seg_last.x + seg_last.y;
+  const int n_blocks = (ke - ks + kBlockKeys - 1) / kBlockKeys;
+
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_slot;
+  const uint32_t tmem_row = tmem_base + ((uint32_t)(warp * 32) << 16);
+  const uint32_t idesc1 = make_idesc_bf16(kTileQ, kBlockKeys), idesc2 = make_idesc_bf16(kTileQ, DP);
+  const float scale = 1.4426950408889634f / fmaxf(__ldg(p.tau), p.tau_min);
+
+  float m_run = -INFINITY, l_run = 0.0f;
+  uint32_t ph1 = 0, ph2 = 0;
+
+  for (int blk = 0; blk < n_blocks; ++blk) {
+    const int kb0 = ks + blk * kBlockKeys;
+    if (blk > 0) {            // MMA 2 of the previous block still reads V and P
+      mbar_wait(bar2, ph2);
+      ph2 ^= 1;
+      tc_fence_after();
+    }
+    // ---- gather K (normalised) and V (transposed): two threads per key, each takes half the chunks ----
+    {
+      const int key = tid >> 1, half = tid & 1;
+      const int kp = kb0 + key;
+      const bool k_ok = kp < ke;
+      int32_t krow = 0;
+      if (k_ok) krow = __ldg(p.order + kp);
+      if (half == 0) kws_s[key] = k_ok ? __ldg(&p.pos_seg[kp].x) : -1;
+      // K: the norm needs the whole slice, so both threads read it all (L1 hit) and each writes its half
+      float f[DP];
+      float ss = 0.0f;
+      if (k_ok) {
+        const uint4 *src = reinterpret_cast<const uint4 *>(p.k + (int64_t)krow * p.ld + h * DP);
+#pragma unroll
+        for (int c = 0; c < kChunks; ++c) {
+          const uint4 u = __ldg(src + c);
+          const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            f[c * 8 + 2 * i] = __uint_as_float(w[i] << 16);
+            f[c * 8 + 2 * i + 1] = __uint_as_float(w[i] & 0xffff0000u);
+            ss = fmaf(f[c * 8 + 2 * i], f[c * 8 + 2 * i], ss);
+            ss = fmaf(f[c * 8 + 2 * i + 1], f[c * 8 + 2 * i + 1], ss);
+          }
+        }
+      } else {
+#pragma unroll
+        for (int i = 0; i < DP; ++i) f[i] = 0.0f;
+      }
+      const float inv = 1.0f / fmaxf(sqrtf(ss), 1e-12f);
+#pragma unroll
+      for (int c = 0; c < kChunks; ++c) {
+        if ((c & 1) != half) continue;
+        uint32_t w[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const __nv_bfloat162 hh = __floats2bfloat162_rn(f[c * 8 + 2 * i] * inv, f[c * 8 + 2 * i + 1] * inv);
+          w[i] = *reinterpret_cast<const uint32_t *>(&hh);
+        }
+        *reinterpret_cast<uint4 *>(k_s + core_off(key, c, kSboQ)) = make_uint4(w[0], w[1], w[2], w[3]);
+      }
+      // V^T: element (dim n, key) -> (n/8)*sbo + (key/8)*lbo + (n%8)*16 + (key%8)*2
+      const uint4 *vsrc = reinterpret_cast<const uint4 *>(p.v + (int64_t)krow * p.ldv + h * DP);
+#pragma unroll
+      for (int c = 0; c < kChunks; ++c) {
+        if ((c & 1) != half) continue;
+        uint4 u = make_uint4(0, 0, 0, 0);
+        if (k_ok) u = __ldg(vsrc + c);
+        const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+        uint8_t *dst = v_s + c * kSboV + (key >> 3) * kLbo + (key & 7) * 2;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          *reinterpret_cast<uint16_t *>(dst + (2 * i) * 16) = (uint16_t)(w[i] & 0xffffu);
+          *reinterpret_cast<uint16_t *>(dst + (2 * i + 1) * 16) = (uint16_t)(w[i] >> 16);
+        }
+      }
+    }
+    fence_proxy_async();
+    tc_fence_before();
+    __syncthreads();
+    if (tid == 0) {
+      tc_fence_after();
+#pragma unroll
+      for (int s = 0; s < DP / 16; ++s)
+        umma_bf16(tmem_base, make_kmajor_nosw_desc(smem_u32(q_s) + s * 2 * kLbo, kLbo, kSboQ),
+                  make_kmajor_nosw_desc(smem_u32(k_s) + s * 2 * kLbo, kLbo, kSboQ), idesc1, s > 0 ? 1u : 0u);
+      umma_commit(bar1);
+    }
+    mbar_wait(bar1, ph1);
+    ph1 ^= 1;
+    tc_fence_after();
+
+    // ---- softmax on this thread's row ----
+    float s[kBlockKeys];
+    {
+      uint32_t r[32];
+      tmem_ld32(tmem_row, r);
+      tmem_ld_wait();
+#pragma unroll
+      for (int i = 0; i < 32; ++i) s[i] = __uint_as_float(r[i]);
+      tmem_ld32(tmem_row + 32, r);
+      tmem_ld_wait();
+#pragma unroll
+      for (int i = 0; i < 32; ++i) s[32 + i] = __uint_as_float(r[i]);
+    }
+    float m_new = m_run;
+#pragma unroll
+    for (int j = 0; j < kBlockKeys; ++j) {
+      s[j] = (kws_s[j] == qws) ? s[j] * scale : -INFINITY;
+      m_new = fmaxf(m_new, s[j]);
+    }
+    const float m_use = (m_new == -INFINITY) ? 0.0f : m_new;      // fully masked so far: exp2(-inf - 0) = 0
+    const float alpha = exp2f(m_run - m_use);                      // m_run = -inf -> 0 (l_run, O are still 0 then)
+    float l_blk = 0.0f;
+    uint32_t pk[kBlockKeys / 2];
+#pragma unroll
+    for (int j = 0; j < kBlockKeys; j += 2) {
+      const float a = exp2f(s[j] - m_use), b = exp2f(s[j + 1] - m_use);
+      const __nv_bfloat162 hh = __floats2bfloat162_rn(a, b);
+      // sum what the tensor core will actually multiply (the bf16-rounded probabilities)
+      l_blk += __low2float(hh) + __high2float(hh);
+      pk[j >> 1] = *reinterpret_cast<const uint32_t *>(&hh);
+    }
+    l_run = l_run * alpha + l_blk;
+    m_run = m_new;
+#pragma unroll
+    for (int c = 0; c < kBlockKeys / 8; ++c)
+      *reinterpret_cast<uint4 *>(p_s + core_off(tid, c, kSboP)) = make_uint4(pk[4 * c], pk[4 * c + 1], pk[4 * c + 2], pk[4 * c + 3]);
+    // rescale O if any row of this warp moved its maximum (tcgen05.ld / st are warp-collective)
+    if (blk > 0 && __any_sync(0xffffffffu, alpha != 1.0f)) {
+#pragma unroll
+      for (int c0 = 0; c0 < DP; c0 += 16) {
+        uint32_t o[16];
+        tmem_ld16(tmem_row + kBlockKeys + c0, o);
+        tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 16; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
+        tmem_st16(tmem_row + kBlockKeys + c0, o);
+      }
+      tmem_st_wait();
+    }
+    fence_proxy_async();
+    tc_fence_before();
+    __syncthreads();
+    if (tid == 0) {
+      tc_fence_after();
+#pragma unroll
+      for (int s2 = 0; s2 < kBlockKeys / 16; ++s2)
+        umma_bf16(tmem_base + kBlockKeys, make_kmajor_nosw_desc(smem_u32(p_s) + s2 * 2 * kLbo, kLbo, kSboP),
+                  make_kmajor_nosw_desc(smem_u32(v_s) + s2 * 2 * kLbo, kLbo, kSboV), idesc2, (blk > 0 || s2 > 0) ? 1u : 0u);
+      umma_commit(bar2);
+    }
+  }
+
+  // ---- epilogue ----
+  mbar_wait(bar2, ph2);
+  tc_fence_after();
+  {
+    const float inv_l = l_run > 0.0f ? 1.0f / l_run : 0.0f;
+    __nv_bfloat16 *dst = p.out + (int64_t)qrow * p.ldo + h * DP;
+#pragma unroll
+    for (int c0 = 0; c0 < DP; c0 += 16) {
+      uint32_t o[16];
+      tmem_ld16(tmem_row + kBlockKeys + c0, o);
+      tmem_ld_wait();
+      if (q_ok) {
+        uint32_t w[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const __nv_bfloat162 hh = __floats2bfloat162_rn(__uint_as_float(o[2 * i]) * inv_l, __uint_as_float(o[2 * i + 1]) * inv_l);
+          w[i] = *reinterpret_cast<const uint32_t *>(&hh);
+        }
+        reinterpret_cast<uint4 *>(dst + c0)[0] = make_uint4(w[0], w[1], w[2], w[3]);
+        reinterpret_cast<uint4 *>(dst + c0)[1] = make_uint4(w[4], w[5], w[6], w[7]);
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, kTmemCols);
+  }
+}
+
+}  // namespace attn_tc
+}  // namespace os3d
+
+using namespace os3d;
+
+extern "C" int os3d_window_attention_bf16_tc(const void *q, const void *k, const void *v, int64_t ld, int64_t ldv,
+                                             int64_t m, int heads, int dp, const int32_t *order, const int32_t *pos_seg,
+                                             const int32_t *level_info, const float *tau, float tau_min, void *out,
+                                             int64_t ldo, void *stream) {
+  if (m == 0) return 0;
+  if (heads <= 0 || (dp != 16 && dp != 32 && dp != 48) || ld % 8 || ldv % 8 || ldo % 8) return OS3D_ERR_BAD_ARG;
+  attn_tc::Params p;
+  p.q = (const __nv_bfloat16 *)q;
+  p.k = (const __nv_bfloat16 *)k;
+  p.v = (const __nv_bfloat16 *)v;
+  p.ld = ld; p.ldv = ldv; p.ldo = ldo;
+  p.order = order;
+  p.pos_seg = (const int2 *)pos_seg;
+  p.level_info = level_info;
+  p.tau = tau;
+  p.tau_min = tau_min;
+  p.out = (__nv_bfloat16 *)out;
+  p.heads = heads;
+  dim3 grid((unsigned)cdiv(m, attn_tc::kTileQ), (unsigned)heads);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (dp == 16) attn_tc::window_attention_tc_kernel<16><<<grid, attn_tc::kThreads, 0, st>>>(p);
+  else if (dp == 32) attn_tc::window_attention_tc_kernel<32><<<grid, attn_tc::kThreads, 0, st>>>(p);
+  else attn_tc::window_attention_tc_kernel<48><<<grid, attn_tc::kThreads, 0, st>>>(p);
+  OS3D_LAUNCH_CHECK();
+  return 0;
+}

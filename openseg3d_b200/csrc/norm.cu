@@ -1,0 +1,131 @@
+// norm.cu -- stage 4 glue: fused residual + LayerNorm for the SWFormer encoder layer (post-norm):
+//   out = resid + LayerNorm(x) * w + b          (seg3d/models/layers/point_transformer_layer.py:288-298:
+//   x = shortcut + drop_path(norm1(attn(x)));  x = x + drop_path(norm2(mlp(x))))
+// Rows are short (C = 48..384), so a row is owned by a sub-warp group of G lanes (G = 8/16/32), every lane moves
+// 16-byte vectors, mean / variance are reduced with shuffles inside the group: one pass over HBM, 3 tensors touched
+// (x, resid, out) instead of the 5 passes of layer_norm + add, and no one-CTA-per-row launch.
+#include "common.cuh"
+
+namespace os3d {
+
+template <typename T> struct Vec8;   // 8 elements = one 16-byte (bf16) or two 16-byte (f32) accesses
+template <> struct Vec8<__nv_bfloat16> {
+  static __device__ __forceinline__ void load(const __nv_bfloat16 *p, float *v) {
+    const uint4 u = __ldg(reinterpret_cast<const uint4 *>(p));
+    const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { v[2 * i] = __uint_as_float(w[i] << 16); v[2 * i + 1] = __uint_as_float(w[i] & 0xffff0000u); }
+  }
+  static __device__ __forceinline__ void store(__nv_bfloat16 *p, const float *v) {
+    uint32_t w[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const __nv_bfloat162 h = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
+      w[i] = *reinterpret_cast<const uint32_t *>(&h);
+    }
+    *reinterpret_cast<uint4 *>(p) = make_uint4(w[0], w[1], w[2], w[3]);
+  }
+};
+template <> struct Vec8<float> {
+  static __device__ __forceinline__ void load(const float *p, float *v) {
+    const float4 a = __ldg(reinterpret_cast<const float4 *>(p)), b = __ldg(reinterpret_cast<const float4 *>(p) + 1);
+    v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+  }
+  static __device__ __forceinline__ void store(float *p, const float *v) {
+    reinterpret_cast<float4 *>(p)[0] = make_float4(v[0], v[1], v[2], v[3]);
+    reinterpret_cast<float4 *>(p)[1] = make_float4(v[4], v[5], v[6], v[7]);
+  }
+};
+
+// G lanes per row, each lane owns chunks lane, lane+G, ... (<= kMaxChunks of 8 elements)
+template <typename T, int G, int kMaxChunks>
+__global__ void __launch_bounds__(256) layernorm_residual_kernel(const T *__restrict__ x, const T *__restrict__ resid,
+                                                                  const float *__restrict__ w, const float *__restrict__ b,
+                                                                  int64_t m, int c, float eps, T *__restrict__ out) {
+  const int lane = threadIdx.x % G;
+  const int64_t row = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) / G;
+  const int chunks = c / 8;
+  const bool row_ok = row < m;
+  float v[kMaxChunks][8];
+  float sum = 0.0f;
+#pragma unroll
+  for (int k = 0; k < kMaxChunks; ++k) {
+    const int ch = lane + k * G;
+    if (row_ok && ch < chunks) {
+      Vec8<T>::load(x + row * c + ch * 8, v[k]);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) sum += v[k][i];
+    } else {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) v[k][i] = 0.0f;
+    }
+  }
+#pragma unroll
+  for (int o = G / 2; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+  const float mean = sum / (float)c;
+  float var = 0.0f;
+#pragma unroll
+  for (int k = 0; k < kMaxChunks; ++k) {
+    const int ch = lane + k * G;
+    if (ch < chunks) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) { const float d = v[k][i] - mean; var = fmaf(d, d, var); }
+    }
+  }
+#pragma unroll
+  for (int o = G / 2; o > 0; o >>= 1) var += __shfl_xor_sync(0xffffffffu, var, o);
+  const float rstd = rsqrtf(var / (float)c + eps);
+  if (!row_ok) return;
+#pragma unroll
+  for (int k = 0; k < kMaxChunks; ++k) {
+    const int ch = lane + k * G;
+    if (ch < chunks) {
+      float r[8], y[8];
+      if (resid) Vec8<T>::load(resid + row * c + ch * 8, r);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int col = ch * 8 + i;
+        y[i] = (v[k][i] - mean) * rstd * __ldg(w + col) + __ldg(b + col);
+        if (resid) y[i] += r[i];
+      }
+      Vec8<T>::store(out + row * c + ch * 8, y);
+    }
+  }
+}
+
+template <typename T>
+static int launch_ln(const T *x, const T *resid, const float *w, const float *b, int64_t m, int c, float eps, T *out,
+                     cudaStream_t st) {
+  const int chunks = c / 8;
+#define OS3D_LN(G, K)                                                                                                \
+  layernorm_residual_kernel<T, G, K><<<(unsigned)cdiv(m * G, 256), 256, 0, st>>>(x, resid, w, b, m, c, eps, out)
+  if (chunks <= 8) OS3D_LN(8, 1);
+  else if (chunks <= 16) OS3D_LN(16, 1);
+  else if (chunks <= 32) OS3D_LN(32, 1);
+  else if (chunks <= 64) OS3D_LN(32, 2);
+  else if (chunks <= 128) OS3D_LN(32, 4);
+  else return OS3D_ERR_BAD_ARG;
+#undef OS3D_LN
+  return 0;
+}
+
+}  // namespace os3d
+
+using namespace os3d;
+
+extern "C" int os3d_layernorm_residual(const void *x, const void *resid, const float *w, const float *b, int64_t m, int c,
+                                       float eps, int elem_size, void *out, void *stream) {
+  if (c <= 0 || c % 8) return OS3D_ERR_BAD_ARG;
+  if (m == 0) return 0;
+  int rc;
+  if (elem_size == 4)
+    rc = launch_ln<float>((const float *)x, (const float *)resid, w, b, m, c, eps, (float *)out, (cudaStream_t)stream);
+  else if (elem_size == 2)
+    rc = launch_ln<__nv_bfloat16>((const __nv_bfloat16 *)x, (const __nv_bfloat16 *)resid, w, b, m, c, eps,
+                                  (__nv_bfloat16 *)out, (cudaStream_t)stream);
+  else
+    return OS3D_ERR_BAD_ARG;
+  if (rc) return rc;
+  OS3D_LAUNCH_CHECK();
+  return 0;
+}

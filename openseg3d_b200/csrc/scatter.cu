@@ -75,6 +75,41 @@ __global__ void scatter_add_kernel(const float *__restrict__ feats, const int64_
   }
 }
 
+// Few destination rows (the SE layer pools 1.45 M points into `batch` rows): per-address atomics would serialise, so
+// every thread keeps a private float4 running sum over a strided set of rows, flushing to L2 only when the id changes
+// (ids arrive sorted by frame) and once at the end.  kRowsPerBlock rows per CTA.
+constexpr int kSmallMRows = 4096;
+__global__ void __launch_bounds__(256) scatter_add_runs_kernel(const float *__restrict__ feats,
+                                                              const int64_t *__restrict__ ids, int64_t n, int c, int cv,
+                                                              float *__restrict__ out, int32_t *__restrict__ counts,
+                                                              int64_t m) {
+  const int col = threadIdx.x % cv;                 // float4 column owned by this thread
+  const int lane_row = threadIdx.x / cv, row_step = 256 / cv;
+  if (lane_row >= row_step) return;
+  const int64_t row_end = min(n, (int64_t)(blockIdx.x + 1) * kSmallMRows);
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  int64_t cur = -1;
+  int cnt = 0;
+  for (int64_t row = (int64_t)blockIdx.x * kSmallMRows + lane_row; row < row_end; row += row_step) {
+    const int64_t id = __ldg(ids + row);
+    if (id < 0 || id >= m) continue;
+    if (id != cur) {
+      if (cur >= 0) {
+        red_add_v4(out + cur * c + col * 4, acc);
+        if (col == 0 && counts) atomicAdd(counts + cur, cnt);
+      }
+      cur = id; acc = make_float4(0.f, 0.f, 0.f, 0.f); cnt = 0;
+    }
+    const float4 v = __ldg(reinterpret_cast<const float4 *>(feats + row * c) + col);
+    acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+    ++cnt;
+  }
+  if (cur >= 0) {
+    red_add_v4(out + cur * c + col * 4, acc);
+    if (col == 0 && counts) atomicAdd(counts + cur, cnt);
+  }
+}
+
 __global__ void mean_normalize_kernel(float *__restrict__ out, const int32_t *__restrict__ counts, int64_t m, int c) {
   const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= m * c) return;
@@ -156,7 +191,9 @@ extern "C" int os3d_scatter_mean_f32(const float *feats, const int64_t *ids, int
   OS3D_CUDA(cudaMemsetAsync(out, 0, sizeof(float) * (size_t)(m * c), st));
   if (counts) OS3D_CUDA(cudaMemsetAsync(counts, 0, sizeof(int32_t) * (size_t)m, st));
   if (n > 0) {
-    if (c % 4 == 0)
+    if (c % 4 == 0 && c / 4 <= 256 && m <= 64 && !counts_in)
+      scatter_add_runs_kernel<<<grid_for(n, kSmallMRows), 256, 0, st>>>(feats, ids, n, c, c / 4, out, counts, m);
+    else if (c % 4 == 0)
       scatter_add_kernel<true><<<grid_for(n * (c / 4), 256), 256, 0, st>>>(feats, ids, n, c, c / 4, out, counts, counts_in, m);
     else
       scatter_add_kernel<false><<<grid_for(n * c, 256), 256, 0, st>>>(feats, ids, n, c, c, out, counts, counts_in, m);

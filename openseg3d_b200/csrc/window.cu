@@ -161,6 +161,7 @@ __global__ void __launch_bounds__(kSortWarps * 32) win_sort_kernel(const int64_t
                                                                    int32_t *__restrict__ level,
                                                                    int32_t *__restrict__ win_rank,
                                                                    int32_t *__restrict__ inner,
+                                                                   int2 *__restrict__ pos_seg,
                                                                    int32_t *__restrict__ level_info, int64_t n_win) {
   __shared__ int32_t buf[kSortWarps][kMaxSeg];
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
@@ -173,6 +174,7 @@ __global__ void __launch_bounds__(kSortWarps * 32) win_sort_kernel(const int64_t
   const int first_of_level = level_info[4 + lvl];
   if (lane == 0) seg_len[slot] = n;
   int32_t *seg = order + off;
+  for (int t = lane; t < n; t += 32) pos_seg[off + t] = make_int2(off, n);  // (window start, length) per position
   const int cap = cfg.lvl_tokens[lvl];
   int dropped = 0;
   if (n <= kMaxSeg) {
@@ -216,24 +218,45 @@ __global__ void mark_unassigned_kernel(const int64_t *__restrict__ win_id, int64
 //   channel j of axis a (a: 0 = x, 1 = y, 2 = z; pos_length = c/3 channels each):
 //     angle = (coord_a - win_a/2) / temperature^(2*floor(j/2)/pos_length);  even j -> sin, odd j -> cos
 template <typename T>
-__global__ void pos_embed_kernel(const int32_t *__restrict__ in_win, int64_t m, int c, int pos_len, float hx, float hy,
-                                 float hz, float temperature, T *__restrict__ out) {
+__global__ void __launch_bounds__(256) pos_embed_kernel(const int32_t *__restrict__ in_win, int64_t m, int c, int pos_len,
+                                                         float hx, float hy, float hz, float temperature,
+                                                         T *__restrict__ out) {
+  // one thread per (row, channel pair): channels (2q, 2q+1) of an axis share the angle -> sin, cos.
+  // inv_freq depends only on the pair index inside an axis: a shared table, filled once per block.
+  __shared__ float inv_freq[256];
+  const int half = (pos_len + 1) / 2;
+  for (int q = threadIdx.x; q < half; q += blockDim.x)
+    inv_freq[q] = powf(temperature, (float)(2 * q) / (float)pos_len);
+  __syncthreads();
+  const int pairs_per_row = (c + 1) / 2;
   const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (t >= m * c) return;
-  const int64_t i = t / c;
-  const int ch = (int)(t - i * c);
-  float val = 0.0f;
-  const int a = ch / pos_len;
-  if (a < 3) {
-    const int j = ch - a * pos_len;
-    // in_win is (z, y, x); axis order of the embedding is x, y, z
-    const float coord = (float)__ldg(in_win + i * 3 + (2 - a)) - (a == 0 ? hx : (a == 1 ? hy : hz));
-    const float inv_freq = powf(temperature, (float)(2 * (j / 2)) / (float)pos_len);
-    const float ang = coord / inv_freq;
-    val = (j & 1) ? cosf(ang) : sinf(ang);
+  if (t >= m * pairs_per_row) return;
+  const int64_t i = t / pairs_per_row;
+  const int ch0 = (int)(t - i * pairs_per_row) * 2;
+  float v[2] = {0.0f, 0.0f};
+#pragma unroll
+  for (int e = 0; e < 2; ++e) {
+    const int ch = ch0 + e;
+    const int a = ch / pos_len;
+    if (ch < c && a < 3) {
+      const int j = ch - a * pos_len;
+      // in_win is (z, y, x); the embedding's axis order is x, y, z
+      const float coord = (float)__ldg(in_win + i * 3 + (2 - a)) - (a == 0 ? hx : (a == 1 ? hy : hz));
+      const float ang = coord / inv_freq[j >> 1];
+      v[e] = (j & 1) ? cosf(ang) : sinf(ang);
+    }
   }
-  if constexpr (sizeof(T) == 4) out[t] = val;
-  else out[t] = __float2bfloat16(val);
+  if constexpr (sizeof(T) == 4) {
+    out[i * c + ch0] = v[0];
+    if (ch0 + 1 < c) out[i * c + ch0 + 1] = v[1];
+  } else {
+    if (!(c & 1)) {
+      *reinterpret_cast<__nv_bfloat162 *>(out + i * c + ch0) = __floats2bfloat162_rn(v[0], v[1]);
+    } else {
+      out[i * c + ch0] = __float2bfloat16(v[0]);
+      if (ch0 + 1 < c) out[i * c + ch0 + 1] = __float2bfloat16(v[1]);
+    }
+  }
 }
 
 }  // namespace os3d
@@ -243,7 +266,7 @@ using namespace os3d;
 static int partition_common(const int64_t *win_id, int64_t m, int64_t n_win, const os3d_window_cfg_t &cfg,
                             int32_t *win_count, int32_t *win_meta, int32_t *block_sums, int64_t n_blocks,
                             int32_t *level, int32_t *win_rank, int32_t *inner, int32_t *order, int32_t *seg_start,
-                            int32_t *seg_len, int32_t *level_info, cudaStream_t st) {
+                            int32_t *seg_len, int32_t *pos_seg, int32_t *level_info, cudaStream_t st) {
   const unsigned gv = (unsigned)cdiv(m, 256);
   win_count_kernel<<<(unsigned)n_blocks, kScanThreads, 0, st>>>(win_count, n_win, cfg, block_sums);
   scan_block_sums_multi_kernel<<<1, kScanThreads, 0, st>>>(block_sums, n_blocks, kLanes);
@@ -253,7 +276,7 @@ static int partition_common(const int64_t *win_id, int64_t m, int64_t n_win, con
   mark_unassigned_kernel<<<gv, 256, 0, st>>>(win_id, m, win_meta, level, win_rank, inner);
   win_sort_kernel<<<(unsigned)cdiv(n_win, kSortWarps), kSortWarps * 32, 0, st>>>(win_id, win_meta, win_count, cfg, order,
                                                                                   seg_len, level, win_rank, inner,
-                                                                                  level_info, n_win);
+                                                                                  (int2 *)pos_seg, level_info, n_win);
   OS3D_LAUNCH_CHECK();
   return 0;
 }
@@ -262,7 +285,7 @@ extern "C" int os3d_window_partition(const int32_t *idx, int64_t m, int batch, c
                                      int32_t *win_count, int32_t *win_meta, int32_t *block_sums, int64_t n_blocks,
                                      int64_t *win_id, int32_t *in_win, int32_t *level, int32_t *win_rank,
                                      int32_t *inner, int32_t *order, int32_t *seg_start, int32_t *seg_len,
-                                     int32_t *level_info, void *stream) {
+                                     int32_t *pos_seg, int32_t *level_info, void *stream) {
   cudaStream_t st = (cudaStream_t)stream;
   const os3d_window_cfg_t cfg = *cfg_p;
   const int64_t n_win = (int64_t)batch * cfg.nwin_x * cfg.nwin_y * cfg.nwin_z;
@@ -272,13 +295,14 @@ extern "C" int os3d_window_partition(const int32_t *idx, int64_t m, int batch, c
   if (m == 0) return 0;
   win_assign_kernel<<<(unsigned)cdiv(m, 256), 256, 0, st>>>((const int4 *)idx, m, cfg, win_id, in_win, win_count);
   return partition_common(win_id, m, n_win, cfg, win_count, win_meta, block_sums, n_blocks, level, win_rank, inner, order,
-                          seg_start, seg_len, level_info, st);
+                          seg_start, seg_len, pos_seg, level_info, st);
 }
 
 extern "C" int os3d_group_partition(const int64_t *group, int64_t n, int64_t n_groups, const os3d_window_cfg_t *cfg_p,
                                     int32_t *count, int32_t *meta, int32_t *block_sums, int64_t n_blocks,
                                     int32_t *level, int32_t *group_rank, int32_t *inner, int32_t *order,
-                                    int32_t *seg_start, int32_t *seg_len, int32_t *level_info, void *stream) {
+                                    int32_t *seg_start, int32_t *seg_len, int32_t *pos_seg, int32_t *level_info,
+                                    void *stream) {
   cudaStream_t st = (cudaStream_t)stream;
   const os3d_window_cfg_t cfg = *cfg_p;
   if (cfg.n_levels < 1 || cfg.n_levels > OS3D_MAX_LEVELS || n_blocks != cdiv(n_groups, kScanTile)) return OS3D_ERR_BAD_ARG;
@@ -287,7 +311,7 @@ extern "C" int os3d_group_partition(const int64_t *group, int64_t n, int64_t n_g
   if (n == 0) return 0;
   group_hist_kernel<<<(unsigned)cdiv(n, 256), 256, 0, st>>>(group, n, count);
   return partition_common(group, n, n_groups, cfg, count, meta, block_sums, n_blocks, level, group_rank, inner, order,
-                          seg_start, seg_len, level_info, st);
+                          seg_start, seg_len, pos_seg, level_info, st);
 }
 
 extern "C" int os3d_pos_embed(const int32_t *in_win, int64_t m, int c, int win_x, int win_y, int win_z,
@@ -295,7 +319,8 @@ extern "C" int os3d_pos_embed(const int32_t *in_win, int64_t m, int c, int win_x
   if (m == 0) return 0;
   const int pos_len = c / 3;
   if (pos_len <= 0) return OS3D_ERR_BAD_ARG;
-  const unsigned g = (unsigned)cdiv(m * c, 256);
+  if (pos_len > 512) return OS3D_ERR_BAD_ARG;
+  const unsigned g = (unsigned)cdiv(m * ((c + 1) / 2), 256);
   cudaStream_t st = (cudaStream_t)stream;
   if (elem_size == 4)
     pos_embed_kernel<float><<<g, 256, 0, st>>>(in_win, m, c, pos_len, win_x / 2.0f, win_y / 2.0f, win_z / 2.0f,

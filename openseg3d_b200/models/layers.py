@@ -135,12 +135,13 @@ class SparseWindowPartitionLayer(nn.Module):
         seg.level, seg.win_rank, seg.inner = torch.empty(m, **i32), torch.empty(m, **i32), torch.empty(m, **i32)
         seg.order = torch.empty(m, **i32)
         seg.seg_start, seg.seg_len = torch.empty(m + 1, **i32), torch.empty(m + 1, **i32)
+        seg.pos_seg = torch.empty((max(m, 1), 2), **i32)
         seg.level_info = torch.empty(16, **i32)
         win_count, win_meta = torch.empty(n_win, **i32), torch.empty(n_win * 3, **i32)
         block_sums = torch.empty((nb + 1) * 5, **i32)
         _lib.call('os3d_window_partition', indices, m, batch_size, ctypes.byref(cfg), win_count, win_meta, block_sums, nb,
                   seg.win_id, seg.in_win, seg.level, seg.win_rank, seg.inner, seg.order, seg.seg_start, seg.seg_len,
-                  seg.level_info)
+                  seg.pos_seg, seg.level_info)
         return seg
 
     @torch.no_grad()
@@ -195,11 +196,50 @@ class CosineMultiheadAttention(nn.MultiheadAttention):
                 self.in_proj_weight, self.in_proj_bias, self.out_proj.weight, self.out_proj.bias))}
         return self._cast['p']
 
+    def params_head_padded(self, dtype):
+        """Projection weights with every head's d channels padded to dp = ceil(d / 16) * 16 (zero rows / columns), the
+        layout os3d_window_attention_bf16_tc consumes: (w_qk [2*H*dp, C], b_qk, w_v [H*dp, C], b_v, w_out [C, H*dp],
+        b_out, dp).  Zero padding changes neither dot products nor norms."""
+        tag = (dtype, self.in_proj_weight._version, self.out_proj.weight._version, self.in_proj_weight.data_ptr())
+        if self._cast.get('pad_tag') != tag:
+            c, h = self.embed_dim, self.num_heads
+            d = c // h
+            dp = (d + 15) // 16 * 16
+            w_in, b_in = self.in_proj_weight.detach().float(), self.in_proj_bias.detach().float()
+
+            def pad_rows(w, b):        # [C, C], [C] -> [H*dp, C], [H*dp]
+                wp = w.new_zeros(h, dp, c)
+                wp[:, :d] = w.view(h, d, c)
+                bp = b.new_zeros(h, dp)
+                bp[:, :d] = b.view(h, d)
+                return wp.reshape(h * dp, c), bp.reshape(h * dp)
+
+            wq, bq = pad_rows(w_in[:c], b_in[:c])
+            wk, bk = pad_rows(w_in[c:2 * c], b_in[c:2 * c])
+            wv, bv = pad_rows(w_in[2 * c:], b_in[2 * c:])
+            wo = self.out_proj.weight.detach().float().new_zeros(c, h, dp)
+            wo[:, :, :d] = self.out_proj.weight.detach().float().view(c, h, d)
+            vals = (torch.cat([wq, wk]), torch.cat([bq, bk]), wv, bv, wo.reshape(c, h * dp), self.out_proj.bias.detach().float())
+            self._cast['pad_tag'] = tag
+            self._cast['pad'] = tuple(t.to(dtype).contiguous() for t in vals) + (dp,)
+        return self._cast['pad']
+
     def forward_segments(self, feat, pos, seg):
         """feat, pos: flat [M, C]; seg: WindowSegments.  Returns [M, C]."""
         if self.training and self.dropout > 0:
             raise NotImplementedError('attention dropout (training) is not built yet')
         m, c = feat.shape
+        if feat.dtype == torch.bfloat16 and c // self.num_heads <= 48:
+            # tensor-core path: head-padded projections, normalisation folded into the attention kernel's gather
+            w_qk, b_qk, w_v, b_v, w_o, b_o, dp = self.params_head_padded(feat.dtype)
+            hd = self.num_heads * dp
+            qk = F.linear(feat + pos if pos is not None else feat, w_qk, b_qk)       # [M, 2*H*dp]
+            v = F.linear(feat, w_v, b_v)                                              # [M, H*dp]
+            out = torch.empty((m, hd), dtype=feat.dtype, device=feat.device)
+            _lib.call('os3d_window_attention_bf16_tc', qk, qk.data_ptr() + hd * 2, v, 2 * hd, hd, m, self.num_heads, dp,
+                      seg.order, seg.pos_seg, seg.level_info, self.tau.detach().float().reshape(1), float(self.tau_min),
+                      out, hd)
+            return F.linear(out, w_o, b_o)
         w_in, b_in, w_out, b_out = self.params(feat.dtype)
         qk_in = feat + pos if pos is not None else feat
         qk = F.linear(qk_in, w_in[:2 * c], b_in[:2 * c])           # [M, 2C]: q | k   (q = k = x + pos)
@@ -254,6 +294,19 @@ def layer_norm_in(mod, x):
                         mod.eps)
 
 
+def residual_layer_norm(mod, x, resid):
+    """resid + LayerNorm(x) in one pass (os3d_layernorm_residual); falls back to torch ops for odd widths / training."""
+    c = x.shape[-1]
+    if (c % 8 or c > 1024 or x.dtype not in (torch.float32, torch.bfloat16) or not mod.elementwise_affine
+            or (torch.is_grad_enabled() and (x.requires_grad or mod.weight.requires_grad))):
+        return resid + layer_norm_in(mod, x)
+    x, resid = x.contiguous(), resid.contiguous()
+    out = torch.empty_like(x)
+    _lib.call('os3d_layernorm_residual', x, resid, _cast_like(mod, 'weight', torch.float32),
+              _cast_like(mod, 'bias', torch.float32), x.shape[0], c, float(mod.eps), x.element_size(), out)
+    return out
+
+
 class MLP(nn.Module):
     def __init__(self, in_features, hidden_features=None, out_features=None, drop=0.):
         super().__init__()
@@ -297,8 +350,12 @@ class EncoderLayer(nn.Module):
         self.mlp = MLP(in_features=d_model, hidden_features=mlp_hidden_dim, drop=drop)
 
     def forward(self, x, pos_dict, ind_dict, key_padding_mask_dict=None):
-        x = x + self.drop_path(layer_norm_in(self.norm1, self.win_attn(x, pos_dict, ind_dict, key_padding_mask_dict)))
-        return x + self.drop_path(layer_norm_in(self.norm2, self.mlp(x)))
+        attn = self.win_attn(x, pos_dict, ind_dict, key_padding_mask_dict)
+        if self.training:
+            x = x + self.drop_path(layer_norm_in(self.norm1, attn))
+            return x + self.drop_path(layer_norm_in(self.norm2, self.mlp(x)))
+        x = residual_layer_norm(self.norm1, attn, x)
+        return residual_layer_norm(self.norm2, self.mlp(x), x)
 
 
 class SWFormerBlock(nn.Module):

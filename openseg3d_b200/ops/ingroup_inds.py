@@ -23,13 +23,15 @@ def group_partition(group_inds, n_groups):
     i32 = dict(dtype=torch.int32, device=dev)
     out = dict(level=torch.empty(n, **i32), group_rank=torch.empty(n, **i32), inner=torch.empty(n, **i32),
                order=torch.empty(n, **i32), seg_start=torch.empty(n + 1, **i32), seg_len=torch.empty(n + 1, **i32),
+               pos_seg=torch.empty((max(n, 1), 2), **i32),
                level_info=torch.empty(16, **i32))
     count = torch.empty(max(n_groups, 1), **i32)
     meta = torch.empty(max(n_groups, 1) * 3, **i32)
     block_sums = torch.empty((nb + 1) * 5, **i32)
     import ctypes
     _lib.call('os3d_group_partition', g, n, n_groups, ctypes.byref(cfg), count, meta, block_sums, nb, out['level'],
-              out['group_rank'], out['inner'], out['order'], out['seg_start'], out['seg_len'], out['level_info'])
+              out['group_rank'], out['inner'], out['order'], out['seg_start'], out['seg_len'], out['pos_seg'],
+              out['level_info'])
     return out
 
 

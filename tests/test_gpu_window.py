@@ -116,3 +116,41 @@ def test_partition_empty_and_single():
     with torch.no_grad():
         out = blk(info)
     assert out.shape == (1, 48) and bool(torch.isfinite(out).all())
+
+
+@pytest.mark.parametrize('c', [48, 96, 192, 384])
+def test_attention_tensor_core_bf16_vs_fp32_path(c):
+    """tcgen05 attention (bf16, head-padded, in-kernel normalisation, online softmax with TMEM rescale) against the
+    fp32 SIMT path that the reference golden pins; windows from 1 to several hundred tokens (multi key-block tiles)."""
+    from openseg3d_b200 import spconv
+    from openseg3d_b200.models import SparseWindowPartitionLayer, WindowAttention
+    rng = np.random.default_rng(c)
+    torch.manual_seed(c)
+    binfo = {0: {'max_tokens': 16, 'batching_range': (0, 16)}, 1: {'max_tokens': 64, 'batching_range': (16, 64)},
+             2: {'max_tokens': 256, 'batching_range': (64, 256)}, 3: {'max_tokens': 800, 'batching_range': (256, 100000)}}
+    coords = []
+    for b in range(2):
+        dense = rng.integers(0, [8, 20, 20], (2600, 3))            # ~4 windows x ~500 tokens
+        mid = rng.integers(0, [16, 60, 60], (2500, 3)) + np.array([0, 40, 40])
+        sparse = rng.integers(0, [16, 200, 200], (1500, 3))
+        cc = np.unique(np.concatenate([dense, mid, sparse]), axis=0)
+        cc = cc[rng.permutation(len(cc))]
+        coords.append(np.pad(cc, ((0, 0), (1, 0)), constant_values=b))
+    coords = torch.from_numpy(np.concatenate(coords).astype(np.int32)).cuda()
+    feats = torch.randn(coords.shape[0], c, device='cuda').bfloat16()
+    layer = SparseWindowPartitionLayer(binfo, (10, 10, 8), (200, 200, 16))
+    attn = WindowAttention(c, 8, 0.0).cuda().eval()
+    with torch.no_grad():
+        attn.self_attn.tau.fill_(0.2)
+        for prm in attn.parameters():                              # bf16-representable weights: isolate kernel error
+            prm.copy_(prm.bfloat16().float())
+        info32 = layer(spconv.SparseConvTensor(feats.float(), coords, [16, 200, 200], 2))
+        info16 = layer(spconv.SparseConvTensor(feats, coords, [16, 200, 200], 2))
+        for s in range(2):
+            ref = attn(feats.float(), info32[f'pos_dict_shift{s}'], info32[f'flat2win_inds_shift{s}'])
+            out = attn(feats, info16[f'pos_dict_shift{s}'], info16[f'flat2win_inds_shift{s}'])
+            seg = info16[f'flat2win_inds_shift{s}']['segments']
+            assert int(seg.seg_len[:int(seg.level_info[13])].max()) > (400 if s == 0 else 200)   # many key blocks
+            err = (out.float() - ref).abs().max().item() / ref.abs().max().item()
+            mean_err = (out.float() - ref).abs().mean().item() / ref.abs().mean().item()
+            assert err < 3e-2 and mean_err < 1e-2, (s, err, mean_err)
