@@ -10,8 +10,9 @@
 //   warps 0-3  producers : gather.  Thread t owns 16-byte chunk (t & 7) of rows (t >> 3) + 16 j; each chunk is one
 //              cp.async (LDGSTS, zero-fill when the row has no neighbour at that offset) straight into the swizzled
 //              K-major UMMA layout; 8 lanes cover one 128-byte row, so every global request is a full line.
-//              Completion is tracked per stage with cp.async groups -> fence.proxy.async -> mbarrier arrive, two stages
-//              behind the issue point so loads stay in flight.
+//              Completion is signalled by cp.async.mbarrier.arrive.noinc on the stage's full barrier, so producers never
+//              wait on their own loads (a per-stage fence.proxy.async in the producers costs a MEMBAR that drains the
+//              in-flight LDGSTS: measured 1.5 us per K-block); the proxy fence is executed by the MMA thread instead.
 //              Weights: the packed image is stored in global memory already swizzled, one contiguous [Cout x 128 B]
 //              slab per K-block, so ONE cp.async.bulk (TMA bulk copy, mbarrier complete_tx) by one thread fills B.
 //   warp 4     MMA issuer : one thread issues tcgen05.mma.kind::f16 (4 K-steps x N-parts per block), commits the
@@ -35,7 +36,6 @@ constexpr int kBlockK = 64;                        // bf16 elements per K-block 
 constexpr int kATileBytes = kTileM * 128;          // 16 KB
 constexpr int kProducerThreads = 128;
 constexpr int kThreads = 160;
-constexpr int kLag = 2;                            // producer arrives this many stages behind its cp.async issue
 constexpr int kMaxStages = 6;
 
 struct Params {
@@ -45,6 +45,8 @@ struct Params {
   int cin;              // feature row pitch in elements (multiple of 8)
   int cout;             // multiple of 16, <= 512
   const __nv_bfloat16 *w_img;
+  const int32_t *chunk_tab;   // [n_blocks * 8]: (offset k << 16) | first channel of the 16-byte chunk, -1 beyond K
+  const uint32_t *blk_mask;   // [n_blocks]: bit mask of the kernel offsets a K-block touches
   int n_blocks;         // ceil(27 * cin / 64)
   int chunks_per_offset;  // cin / 8
   int total_chunks;     // 27 * cin / 8
@@ -58,13 +60,6 @@ struct Params {
   uint32_t idesc;       // tcgen05 instruction descriptor (bf16 x bf16 -> f32, M=128, N=n_per_part, K-major A and B)
   int stages;
 };
-
-// offsets (bit mask over the 27 kernel offsets) that K-block `blk` touches
-__device__ __forceinline__ uint32_t block_offsets(int blk, int cpo, int total_chunks) {
-  const int first = (blk * 8) / cpo;
-  const int last = min(blk * 8 + 7, total_chunks - 1) / cpo;
-  return (uint32_t)(((1ull << (last + 1)) - 1) & ~((1ull << first) - 1));
-}
 
 __global__ void __launch_bounds__(kThreads) spconv_tc_kernel(const Params p) {
   extern __shared__ uint8_t smem_raw[];
@@ -112,44 +107,44 @@ __global__ void __launch_bounds__(kThreads) spconv_tc_kernel(const Params p) {
   tc_fence_after();
   const uint32_t tmem_base = misc[0];
   const uint32_t has_k = misc[1];
-  const int cpo = p.chunks_per_offset;
 
   if (warp < 4) {
     // ================================ producers ================================
+    // Per-thread invariants: chunk c of rows r0 + 16 j.  Everything that does not depend on the K-block is hoisted;
+    // the (offset, channel) of a chunk comes from a per-layer table written next to the weight image, so the loop
+    // body is: table load, then per row { LDS neighbour, multiply-add address, LDGSTS }.
     const int c = tid & 7, r0 = tid >> 3;
-    int it = 0;
+    const uint32_t dst0 = (uint32_t)(r0 * 128 + ((c ^ (r0 & 7)) << 4));      // row r0 + 16 j -> + j * 2048
+    const int32_t *nrow = nbr_s + r0 * OS3D_KVOL;                           // row r0 + 16 j -> + j * 16 * 27
+    const char *in_bytes = reinterpret_cast<const char *>(p.in);
+    const uint32_t row_bytes = (uint32_t)p.cin * 2u;
+    const int32_t *tab = p.chunk_tab + c;
+    int it = 0, stage = 0;
+    uint32_t phase = 1;                                                     // empty barriers start "free"
     for (int blk = 0; blk < p.n_blocks; ++blk) {
-      if (!(block_offsets(blk, cpo, p.total_chunks) & has_k)) continue;
-      const int stage = it % p.stages;
-      mbar_wait(empty0 + 8 * stage, ((it / p.stages) & 1) ^ 1);
+      if (!(__ldg(p.blk_mask + blk) & has_k)) continue;
+      mbar_wait(empty0 + 8 * stage, phase);
       if (tid == 0) {
         mbar_arrive_expect_tx(full0 + 8 * stage, (uint32_t)b_tile_bytes);
         bulk_g2s(b_base + stage * b_tile_bytes, p.w_img + (int64_t)blk * p.cout * kBlockK, (uint32_t)b_tile_bytes,
                  full0 + 8 * stage);
       }
-      const int g = blk * 8 + c;
-      const bool chunk_ok = g < p.total_chunks;
-      const int koff = chunk_ok ? g / cpo : 0;
-      const int cc = g - koff * cpo;
-      const uint32_t a_stage = a_base + stage * kATileBytes;
+      const int32_t t = __ldg(tab + blk * 8);
+      const int koff = t >> 16;                        // -1 when the chunk lies beyond 27 * cin (t == -1)
+      const uint32_t ch_bytes = (uint32_t)(t & 0xffff) * 2u;
+      const uint32_t a_dst = a_base + stage * kATileBytes + dst0;
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
-        const int row = r0 + 16 * j;
-        const int32_t n = chunk_ok ? nbr_s[row * OS3D_KVOL + koff] : -1;
-        const __nv_bfloat16 *src = p.in + (n >= 0 ? (int64_t)n * p.cin + cc * 8 : 0);
-        cp_async_16(a_stage + row * 128 + ((c ^ (row & 7)) << 4), src, n >= 0 ? 16u : 0u);
+        const int32_t n = t >= 0 ? nrow[j * 16 * OS3D_KVOL + koff] : -1;
+        const char *src = in_bytes + ((uint64_t)((uint32_t)max(n, 0) * row_bytes) + ch_bytes);
+        cp_async_16(a_dst + j * 2048, src, n >= 0 ? 16u : 0u);
       }
-      cp_async_commit();
-      if (it >= kLag) {
-        cp_async_wait<kLag>();
-        fence_proxy_async();
-        mbar_arrive(full0 + 8 * ((it - kLag) % p.stages));
-      }
+      // asynchronous arrive: fires on the full barrier once this thread's copies above have landed -- the producer
+      // never waits on its own loads and runs ahead until the ring is full
+      cp_async_mbar_arrive_noinc(full0 + 8 * stage);
       ++it;
+      if (++stage == p.stages) { stage = 0; phase ^= 1; }
     }
-    cp_async_wait<0>();
-    fence_proxy_async();
-    for (int d = max(0, it - kLag); d < it; ++d) mbar_arrive(full0 + 8 * (d % p.stages));
 
     // ================================ epilogue ================================
     if (it > 0) {
@@ -172,9 +167,17 @@ __global__ void __launch_bounds__(kThreads) spconv_tc_kernel(const Params p) {
       if (row_ok) {
         float y[16];
 #pragma unroll
-        for (int i = 0; i < 16; ++i) {
-          y[i] = __uint_as_float(v[i]);
-          if (p.scale) y[i] = fmaf(y[i], __ldg(p.scale + col + i), __ldg(p.shift + col + i));
+        for (int i = 0; i < 16; ++i) y[i] = __uint_as_float(v[i]);
+        if (p.scale) {
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const float4 sc = __ldg(reinterpret_cast<const float4 *>(p.scale + col) + q);
+            const float4 sh = __ldg(reinterpret_cast<const float4 *>(p.shift + col) + q);
+            y[4 * q + 0] = fmaf(y[4 * q + 0], sc.x, sh.x);
+            y[4 * q + 1] = fmaf(y[4 * q + 1], sc.y, sh.y);
+            y[4 * q + 2] = fmaf(y[4 * q + 2], sc.z, sh.z);
+            y[4 * q + 3] = fmaf(y[4 * q + 3], sc.w, sh.w);
+          }
         }
         if (rrow) {
           const uint4 ra = __ldg(reinterpret_cast<const uint4 *>(rrow + col));
@@ -202,11 +205,12 @@ __global__ void __launch_bounds__(kThreads) spconv_tc_kernel(const Params p) {
   } else {
     // ================================ MMA issuer ================================
     if (lane == 0) {
-      int it = 0;
+      int it = 0, stage = 0;
+      uint32_t phase = 0;
       for (int blk = 0; blk < p.n_blocks; ++blk) {
-        if (!(block_offsets(blk, cpo, p.total_chunks) & has_k)) continue;
-        const int stage = it % p.stages;
-        mbar_wait(full0 + 8 * stage, (it / p.stages) & 1);
+        if (!(__ldg(p.blk_mask + blk) & has_k)) continue;
+        mbar_wait(full0 + 8 * stage, phase);
+        fence_proxy_async();   // cp.async (generic-proxy) writes observed through the barrier -> visible to the MMA's async proxy
         tc_fence_after();
         const uint32_t a_stage = a_base + stage * kATileBytes;
         const uint32_t b_stage = b_base + stage * b_tile_bytes;
@@ -220,6 +224,7 @@ __global__ void __launch_bounds__(kThreads) spconv_tc_kernel(const Params p) {
         }
         umma_commit(empty0 + 8 * stage);  // frees the stage once the MMAs above have read it
         ++it;
+        if (++stage == p.stages) { stage = 0; phase ^= 1; }
       }
       if (it > 0) umma_commit(accum_bar);  // accumulator complete -> epilogue
     }
@@ -234,21 +239,32 @@ __global__ void __launch_bounds__(kThreads) spconv_tc_kernel(const Params p) {
 }
 
 // spconv 2.x weight [cout, 27, cin] f32  ->  bf16 UMMA image [n_blocks][cout][8 chunks, XOR-swizzled by row & 7][8]:
-// exactly the bytes a K-block's B tile occupies in shared memory, so one bulk copy loads it.
+// exactly the bytes a K-block's B tile occupies in shared memory, so one bulk copy loads it.  Two small per-layer
+// tables follow the image: chunk_tab[n_blocks * 8] and blk_mask[n_blocks] (see Params).
 __global__ void pack_weight_img_kernel(const float *__restrict__ src, int cin, int cout, int cin_pad, int n_blocks,
-                                       __nv_bfloat16 *__restrict__ dst) {
+                                       __nv_bfloat16 *__restrict__ dst, int32_t *__restrict__ chunk_tab,
+                                       uint32_t *__restrict__ blk_mask) {
   const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   const int64_t total = (int64_t)n_blocks * cout * kBlockK;
+  const int cpo = cin_pad / 8;
+  const int total_chunks = OS3D_KVOL * cpo;
+  if (t < n_blocks * 8) {
+    const int g = (int)t;
+    chunk_tab[g] = g < total_chunks ? (((g / cpo) << 16) | ((g % cpo) * 8)) : -1;
+  }
+  if (t < n_blocks) {
+    const int first = ((int)t * 8) / cpo, last = min((int)t * 8 + 7, total_chunks - 1) / cpo;
+    blk_mask[t] = (uint32_t)(((1ull << (last + 1)) - 1) & ~((1ull << first) - 1));
+  }
   if (t >= total) return;
   const int e = (int)(t & 7);
   const int pc = (int)((t >> 3) & 7);
   const int n = (int)((t >> 6) % cout);
   const int blk = (int)((t >> 6) / cout);
   const int c = pc ^ (n & 7);  // logical chunk stored at physical chunk pc
-  const int cpo = cin_pad / 8;
   const int g = blk * 8 + c;
   float v = 0.0f;
-  if (g < OS3D_KVOL * cpo) {
+  if (g < total_chunks) {
     const int koff = g / cpo, ch = (g - koff * cpo) * 8 + e;
     if (ch < cin) v = src[((int64_t)n * OS3D_KVOL + koff) * cin + ch];
   }
@@ -262,7 +278,8 @@ using namespace os3d;
 
 extern "C" int os3d_spconv_bf16_packed_elems(int cin_pad, int cout, int64_t *elems) {
   if (cin_pad <= 0 || cin_pad % 8 || cout <= 0) return OS3D_ERR_BAD_ARG;
-  *elems = cdiv((int64_t)OS3D_KVOL * cin_pad, tc::kBlockK) * cout * tc::kBlockK;
+  const int64_t n_blocks = cdiv((int64_t)OS3D_KVOL * cin_pad, tc::kBlockK);
+  *elems = n_blocks * cout * tc::kBlockK + (n_blocks * 9 * 4 + 64) / 2;   // image + chunk_tab + blk_mask (bf16 units)
   return 0;
 }
 
@@ -271,8 +288,10 @@ extern "C" int os3d_pack_weight_bf16(const float *w_spconv, int cin, int cout, i
   if (cin_pad % 8 || cin_pad < cin) return OS3D_ERR_BAD_ARG;
   const int n_blocks = (int)cdiv((int64_t)OS3D_KVOL * cin_pad, tc::kBlockK);
   const int64_t total = (int64_t)n_blocks * cout * tc::kBlockK;
+  __nv_bfloat16 *img = (__nv_bfloat16 *)w_packed;
+  int32_t *tab = reinterpret_cast<int32_t *>(img + total);               // total * 2 bytes is a multiple of 128
   tc::pack_weight_img_kernel<<<(unsigned)cdiv(total, 256), 256, 0, (cudaStream_t)stream>>>(
-      w_spconv, cin, cout, cin_pad, n_blocks, (__nv_bfloat16 *)w_packed);
+      w_spconv, cin, cout, cin_pad, n_blocks, img, tab, reinterpret_cast<uint32_t *>(tab + n_blocks * 8));
   OS3D_LAUNCH_CHECK();
   return 0;
 }
@@ -292,6 +311,8 @@ extern "C" int os3d_spconv_fwd_bf16(const void *in, const int32_t *nbr, int64_t 
   p.cout = cout;
   p.w_img = (const __nv_bfloat16 *)w;
   p.n_blocks = (int)cdiv((int64_t)OS3D_KVOL * cin, tc::kBlockK);
+  p.chunk_tab = reinterpret_cast<const int32_t *>(p.w_img + (int64_t)p.n_blocks * cout * tc::kBlockK);
+  p.blk_mask = reinterpret_cast<const uint32_t *>(p.chunk_tab + p.n_blocks * 8);
   p.chunks_per_offset = cin / 8;
   p.total_chunks = OS3D_KVOL * cin / 8;
   p.scale = scale;
@@ -309,10 +330,10 @@ extern "C" int os3d_spconv_fwd_bf16(const void *in, const int32_t *nbr, int64_t 
   p.idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.n_per_part >> 3) << 17) | ((uint32_t)(tc::kTileM >> 4) << 24);
   const int stage_bytes = tc::kATileBytes + cout * 128;
   const int tail = tc::kTileM * OS3D_KVOL * 4 + (2 * tc::kMaxStages + 1) * 8 + 64;
-  // small tiles: 3 stages so two CTAs share an SM; large tiles: as many stages as fit one CTA per SM
-  int stages = cout <= 96 ? 3 : (227 * 1024 - 1024 - tail) / stage_bytes;
+  // small tiles: 4 stages so two CTAs share an SM; large tiles: as many stages as fit one CTA per SM
+  int stages = cout <= 48 ? 4 : cout <= 96 ? 3 : (227 * 1024 - 1024 - tail) / stage_bytes;
   stages = stages > tc::kMaxStages ? tc::kMaxStages : stages;
-  if (stages < tc::kLag + 1) return OS3D_ERR_BAD_ARG;
+  if (stages < 2) return OS3D_ERR_BAD_ARG;
   p.stages = stages;
   const int smem = 1024 + stages * stage_bytes + tail;
   static int configured = 0;
