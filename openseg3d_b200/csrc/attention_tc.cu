@@ -43,6 +43,12 @@ struct Params {
   int heads;
 };
 
+__device__ __forceinline__ float ex2_ftz(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
 // smem offset of element chunk (row r, 16-byte K-chunk c) in the K-major no-swizzle layout with 8-row group stride sbo
 __device__ __forceinline__ uint32_t core_off(int r, int c, int sbo) { return (r >> 3) * sbo + c * kLbo + (r & 7) * 16; }
 
@@ -61,7 +67,6 @@ __global__ void __launch_bounds__(kThreads) window_attention_tc_kernel(const Par
   __shared__ __align__(128) uint8_t k_s[kKBytes];
   __shared__ __align__(128) uint8_t v_s[kVBytes];
   __shared__ __align__(128) uint8_t p_s[kPBytes];
-  __shared__ int32_t kws_s[kBlockKeys];                   // window start of each key of the block (-1 = no key)
   __shared__ __align__(8) uint64_t bars[2];
   __shared__ uint32_t tmem_slot;
 
@@ -83,10 +88,12 @@ __global__ void __launch_bounds__(kThreads) window_attention_tc_kernel(const Par
   // ---- this thread's query row ----
   const int qp = p0 + tid;
   const bool q_ok = qp <= p_last;
-  int qws = -2;
+  int qws = 0, qlen = 0;                 // this row's window = grouped positions [qws, qws + qlen)
   int32_t qrow = 0;
   if (q_ok) {
-    qws = __ldg(&p.pos_seg[qp].x);
+    const int2 seg = __ldg(&p.pos_seg[qp]);
+    qws = seg.x;
+    qlen = seg.y;
     qrow = __ldg(p.order + qp);
   }
   {
@@ -142,41 +149,51 @@ __global__ void __launch_bounds__(kThreads) window_attention_tc_kernel(const Par
   float m_run = -INFINITY, l_run = 0.0f;
   uint32_t ph1 = 0, ph2 = 0;
 
+  // Two threads per key; both read the whole K slice (the norm needs it), each stores the chunks c with (c & 1) == half
+  // and transposes the same chunks of V.  The raw slices of block b+1 are fetched into registers while block b is in
+  // its MMA / softmax phases, so the two dependent global loads (order -> row) are off the critical path.
+  const int key = tid >> 1, half = tid & 1;
+  constexpr int kVChunks = (kChunks + 1) / 2;
+  uint4 k_raw[kChunks], v_raw[kVChunks];
+  bool k_ok_next = false;
+  auto prefetch = [&](int blk) {
+    const int kp = ks + blk * kBlockKeys + key;
+    k_ok_next = blk < n_blocks && kp < ke;
+    if (k_ok_next) {
+      const int32_t krow = __ldg(p.order + kp);
+      const uint4 *ksrc = reinterpret_cast<const uint4 *>(p.k + (int64_t)krow * p.ld + h * DP);
+      const uint4 *vsrc = reinterpret_cast<const uint4 *>(p.v + (int64_t)krow * p.ldv + h * DP);
+#pragma unroll
+      for (int c = 0; c < kChunks; ++c) k_raw[c] = __ldg(ksrc + c);
+#pragma unroll
+      for (int c = 0; c < kVChunks; ++c)
+        if (2 * c + half < kChunks) v_raw[c] = __ldg(vsrc + 2 * c + half);
+    }
+  };
+  prefetch(0);
+
   for (int blk = 0; blk < n_blocks; ++blk) {
-    const int kb0 = ks + blk * kBlockKeys;
     if (blk > 0) {            // MMA 2 of the previous block still reads V and P
       mbar_wait(bar2, ph2);
       ph2 ^= 1;
       tc_fence_after();
     }
-    // ---- gather K (normalised) and V (transposed): two threads per key, each takes half the chunks ----
+    // ---- registers -> shared memory: K normalised (K-major), V transposed ----
     {
-      const int key = tid >> 1, half = tid & 1;
-      const int kp = kb0 + key;
-      const bool k_ok = kp < ke;
-      int32_t krow = 0;
-      if (k_ok) krow = __ldg(p.order + kp);
-      if (half == 0) kws_s[key] = k_ok ? __ldg(&p.pos_seg[kp].x) : -1;
-      // K: the norm needs the whole slice, so both threads read it all (L1 hit) and each writes its half
       float f[DP];
       float ss = 0.0f;
-      if (k_ok) {
-        const uint4 *src = reinterpret_cast<const uint4 *>(p.k + (int64_t)krow * p.ld + h * DP);
 #pragma unroll
-        for (int c = 0; c < kChunks; ++c) {
-          const uint4 u = __ldg(src + c);
-          const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+      for (int c = 0; c < kChunks; ++c) {
+        const uint32_t w[4] = {k_raw[c].x, k_raw[c].y, k_raw[c].z, k_raw[c].w};
 #pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            f[c * 8 + 2 * i] = __uint_as_float(w[i] << 16);
-            f[c * 8 + 2 * i + 1] = __uint_as_float(w[i] & 0xffff0000u);
-            ss = fmaf(f[c * 8 + 2 * i], f[c * 8 + 2 * i], ss);
-            ss = fmaf(f[c * 8 + 2 * i + 1], f[c * 8 + 2 * i + 1], ss);
-          }
+        for (int i = 0; i < 4; ++i) {
+          const float a = k_ok_next ? __uint_as_float(w[i] << 16) : 0.0f;
+          const float b2 = k_ok_next ? __uint_as_float(w[i] & 0xffff0000u) : 0.0f;
+          f[c * 8 + 2 * i] = a;
+          f[c * 8 + 2 * i + 1] = b2;
+          ss = fmaf(a, a, ss);
+          ss = fmaf(b2, b2, ss);
         }
-      } else {
-#pragma unroll
-        for (int i = 0; i < DP; ++i) f[i] = 0.0f;
       }
       const float inv = 1.0f / fmaxf(sqrtf(ss), 1e-12f);
 #pragma unroll
@@ -191,12 +208,11 @@ __global__ void __launch_bounds__(kThreads) window_attention_tc_kernel(const Par
         *reinterpret_cast<uint4 *>(k_s + core_off(key, c, kSboQ)) = make_uint4(w[0], w[1], w[2], w[3]);
       }
       // V^T: element (dim n, key) -> (n/8)*sbo + (key/8)*lbo + (n%8)*16 + (key%8)*2
-      const uint4 *vsrc = reinterpret_cast<const uint4 *>(p.v + (int64_t)krow * p.ldv + h * DP);
 #pragma unroll
-      for (int c = 0; c < kChunks; ++c) {
-        if ((c & 1) != half) continue;
-        uint4 u = make_uint4(0, 0, 0, 0);
-        if (k_ok) u = __ldg(vsrc + c);
+      for (int cv = 0; cv < kVChunks; ++cv) {
+        const int c = 2 * cv + half;
+        if (c >= kChunks) continue;
+        const uint4 u = k_ok_next ? v_raw[cv] : make_uint4(0, 0, 0, 0);
         const uint32_t w[4] = {u.x, u.y, u.z, u.w};
         uint8_t *dst = v_s + c * kSboV + (key >> 3) * kLbo + (key & 7) * 2;
 #pragma unroll
@@ -217,11 +233,17 @@ __global__ void __launch_bounds__(kThreads) window_attention_tc_kernel(const Par
                   make_kmajor_nosw_desc(smem_u32(k_s) + s * 2 * kLbo, kLbo, kSboQ), idesc1, s > 0 ? 1u : 0u);
       umma_commit(bar1);
     }
+    prefetch(blk + 1);        // global loads for the next key block fly during MMA 1, the softmax and MMA 2
     mbar_wait(bar1, ph1);
     ph1 ^= 1;
     tc_fence_after();
 
     // ---- softmax on this thread's row ----
+    // A key at grouped position kp is in this row's window iff qws <= kp < qws + qlen, i.e. the valid keys of the block
+    // are the index range [lo, hi): no mask array in memory.  (Skipping the off-diagonal 16-column groups / 8-key chunks
+    // with warp votes was measured SLOWER -- 26.8 vs 20.8 ms per step -- the kernel is latency-, not ALU-bound.)
+    const int kb0 = ks + blk * kBlockKeys;
+    const int lo = max(qws - kb0, 0), hi = min(qws + qlen - kb0, kBlockKeys);
     float s[kBlockKeys];
     {
       uint32_t r[32];
@@ -234,22 +256,27 @@ __global__ void __launch_bounds__(kThreads) window_attention_tc_kernel(const Par
 #pragma unroll
       for (int i = 0; i < 32; ++i) s[32 + i] = __uint_as_float(r[i]);
     }
-    float m_new = m_run;
+    // valid keys as a bit mask: one LOP3 + FSEL per element instead of two compares; the scale and the running maximum
+    // are folded into one FFMA feeding ex2.approx.ftz (masked scores are -inf -> probability exactly 0)
+    const uint64_t valid = hi > lo ? ((~0ull >> (64 - (hi - lo))) << lo) : 0ull;
+    const uint32_t v_lo = (uint32_t)valid, v_hi = (uint32_t)(valid >> 32);
+    float m_new = m_run;                                           // maxima are kept in raw (unscaled) score units
 #pragma unroll
     for (int j = 0; j < kBlockKeys; ++j) {
-      s[j] = (kws_s[j] == qws) ? s[j] * scale : -INFINITY;
+      const bool ok = ((j < 32 ? v_lo : v_hi) >> (j & 31)) & 1u;
+      s[j] = ok ? s[j] : -INFINITY;
       m_new = fmaxf(m_new, s[j]);
     }
-    const float m_use = (m_new == -INFINITY) ? 0.0f : m_new;      // fully masked so far: exp2(-inf - 0) = 0
-    const float alpha = exp2f(m_run - m_use);                      // m_run = -inf -> 0 (l_run, O are still 0 then)
+    const float m_use = (m_new == -INFINITY) ? 0.0f : m_new;      // nothing valid so far: ex2(-inf) = 0 everywhere
+    const float alpha = ex2_ftz((m_run - m_use) * scale);          // m_run = -inf -> 0 (l_run, O are still 0 then)
+    const float neg_ms = -m_use * scale;
     float l_blk = 0.0f;
     uint32_t pk[kBlockKeys / 2];
 #pragma unroll
     for (int j = 0; j < kBlockKeys; j += 2) {
-      const float a = exp2f(s[j] - m_use), b = exp2f(s[j + 1] - m_use);
+      const float a = ex2_ftz(fmaf(s[j], scale, neg_ms)), b = ex2_ftz(fmaf(s[j + 1], scale, neg_ms));
+      l_blk += a + b;
       const __nv_bfloat162 hh = __floats2bfloat162_rn(a, b);
-      // sum what the tensor core will actually multiply (the bf16-rounded probabilities)
-      l_blk += __low2float(hh) + __high2float(hh);
       pk[j >> 1] = *reinterpret_cast<const uint32_t *>(&hh);
     }
     l_run = l_run * alpha + l_blk;

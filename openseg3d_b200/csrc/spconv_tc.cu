@@ -7,7 +7,7 @@
 // is ever scattered or atomically added.  The contraction dimension is the flattened (offset k, input channel) axis,
 // 27*Cin long, cut into 64-element blocks (one 128-byte SWIZZLE_128B row per output row / output channel):
 //
-//   warps 0-3  producers : gather.  Thread t owns 16-byte chunk (t & 7) of rows (t >> 3) + 16 j; each chunk is one
+//   warps 0-7  producers : gather.  Thread t owns 16-byte chunk (t & 7) of rows (t >> 3) + 32 j; each chunk is one
 //              cp.async (LDGSTS, zero-fill when the row has no neighbour at that offset) straight into the swizzled
 //              K-major UMMA layout; 8 lanes cover one 128-byte row, so every global request is a full line.
 //              Completion is signalled by cp.async.mbarrier.arrive.noinc on the stage's full barrier, so producers never
@@ -15,9 +15,9 @@
 //              in-flight LDGSTS: measured 1.5 us per K-block); the proxy fence is executed by the MMA thread instead.
 //              Weights: the packed image is stored in global memory already swizzled, one contiguous [Cout x 128 B]
 //              slab per K-block, so ONE cp.async.bulk (TMA bulk copy, mbarrier complete_tx) by one thread fills B.
-//   warp 4     MMA issuer : one thread issues tcgen05.mma.kind::f16 (4 K-steps x N-parts per block), commits the
+//   warp 8     MMA issuer : one thread issues tcgen05.mma.kind::f16 (4 K-steps x N-parts per block), commits the
 //              stage back to the producers (tcgen05.commit -> empty barrier) and finally signals the epilogue.
-//   warps 0-3  epilogue  : tcgen05.ld 32x32b (lane = output row), y = acc*scale + shift (+ residual) (ReLU), bf16,
+//   warps 0-7  epilogue  : tcgen05.ld 32x32b (lane = output row; warps w and w+4 split the columns), y = acc*scale + shift (+ residual) (ReLU), bf16,
 //              32-byte vector stores.  Bias, eval-mode BatchNorm, the residual add and the ReLU of the reference's
 //              SparseBasicBlock / ConvModule therefore never touch HBM as separate passes.
 //   K-blocks whose offsets have no neighbour anywhere in the tile are skipped by all three roles (same enumeration).
@@ -34,8 +34,9 @@ using namespace ptx;
 constexpr int kTileM = 128;
 constexpr int kBlockK = 64;                        // bf16 elements per K-block = one 128-byte swizzle row
 constexpr int kATileBytes = kTileM * 128;          // 16 KB
-constexpr int kProducerThreads = 128;
-constexpr int kThreads = 160;
+constexpr int kProducerWarps = 8;                  // gather producers, then epilogue (two warps per TMEM lane quarter)
+constexpr int kProducerThreads = kProducerWarps * 32;
+constexpr int kThreads = kProducerThreads + 32;    // + the MMA-issuing warp
 constexpr int kMaxStages = 6;
 
 struct Params {
@@ -90,7 +91,7 @@ __global__ void __launch_bounds__(kThreads) spconv_tc_kernel(const Params p) {
     fence_barrier_init();
   }
   __syncthreads();
-  if (warp == 4) tmem_alloc(smem_u32(&misc[0]), (uint32_t)p.tmem_cols);
+  if (warp == kProducerWarps) tmem_alloc(smem_u32(&misc[0]), (uint32_t)p.tmem_cols);
   {
     uint32_t mask = 0;
     for (int t = tid; t < kTileM * OS3D_KVOL; t += kThreads) {
@@ -108,14 +109,15 @@ __global__ void __launch_bounds__(kThreads) spconv_tc_kernel(const Params p) {
   const uint32_t tmem_base = misc[0];
   const uint32_t has_k = misc[1];
 
-  if (warp < 4) {
+  if (warp < kProducerWarps) {
     // ================================ producers ================================
     // Per-thread invariants: chunk c of rows r0 + 16 j.  Everything that does not depend on the K-block is hoisted;
     // the (offset, channel) of a chunk comes from a per-layer table written next to the weight image, so the loop
     // body is: table load, then per row { LDS neighbour, multiply-add address, LDGSTS }.
+    constexpr int kRowStep = kProducerThreads / 8, kRowsPerThread = kTileM / kRowStep;
     const int c = tid & 7, r0 = tid >> 3;
-    const uint32_t dst0 = (uint32_t)(r0 * 128 + ((c ^ (r0 & 7)) << 4));      // row r0 + 16 j -> + j * 2048
-    const int32_t *nrow = nbr_s + r0 * OS3D_KVOL;                           // row r0 + 16 j -> + j * 16 * 27
+    const uint32_t dst0 = (uint32_t)(r0 * 128 + ((c ^ (r0 & 7)) << 4));      // row r0 + kRowStep j -> + j * kRowStep * 128
+    const int32_t *nrow = nbr_s + r0 * OS3D_KVOL;                           // row r0 + kRowStep j -> + j * kRowStep * 27
     const char *in_bytes = reinterpret_cast<const char *>(p.in);
     const uint32_t row_bytes = (uint32_t)p.cin * 2u;
     const int32_t *tab = p.chunk_tab + c;
@@ -134,10 +136,10 @@ __global__ void __launch_bounds__(kThreads) spconv_tc_kernel(const Params p) {
       const uint32_t ch_bytes = (uint32_t)(t & 0xffff) * 2u;
       const uint32_t a_dst = a_base + stage * kATileBytes + dst0;
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        const int32_t n = t >= 0 ? nrow[j * 16 * OS3D_KVOL + koff] : -1;
+      for (int j = 0; j < kRowsPerThread; ++j) {
+        const int32_t n = t >= 0 ? nrow[j * kRowStep * OS3D_KVOL + koff] : -1;
         const char *src = in_bytes + ((uint64_t)((uint32_t)max(n, 0) * row_bytes) + ch_bytes);
-        cp_async_16(a_dst + j * 2048, src, n >= 0 ? 16u : 0u);
+        cp_async_16(a_dst + j * kRowStep * 128, src, n >= 0 ? 16u : 0u);
       }
       // asynchronous arrive: fires on the full barrier once this thread's copies above have landed -- the producer
       // never waits on its own loads and runs ahead until the ring is full
@@ -151,14 +153,15 @@ __global__ void __launch_bounds__(kThreads) spconv_tc_kernel(const Params p) {
       mbar_wait(accum_bar, 0);
       tc_fence_after();
     }
-    const int row = warp * 32 + lane;
+    const int quarter = warp & 3;                       // TMEM lanes [32 q, 32 q + 32) are visible to warps q and q + 4
+    const int row = quarter * 32 + lane;
     const bool row_ok = row < rows;
     __nv_bfloat16 *orow = p.out + (row0 + row) * p.cout;
     const __nv_bfloat16 *rrow = p.residual ? p.residual + (row0 + row) * p.cout : nullptr;
-    for (int col = 0; col < p.cout; col += 16) {
+    for (int col = (warp >> 2) * 16; col < p.cout; col += 16 * (kProducerWarps / 4)) {
       uint32_t v[16];
       if (it > 0) {
-        tmem_ld16(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)col, v);
+        tmem_ld16(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)col, v);
         tmem_ld_wait();
       } else {
 #pragma unroll
@@ -232,7 +235,7 @@ __global__ void __launch_bounds__(kThreads) spconv_tc_kernel(const Params p) {
     tc_fence_before();
   }
   __syncthreads();
-  if (warp == 4) {
+  if (warp == kProducerWarps) {
     tc_fence_after();
     tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols);
   }
