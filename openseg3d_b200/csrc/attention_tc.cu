@@ -53,7 +53,7 @@ __device__ __forceinline__ float ex2_ftz(float x) {
 __device__ __forceinline__ uint32_t core_off(int r, int c, int sbo) { return (r >> 3) * sbo + c * kLbo + (r & 7) * 16; }
 
 template <int DP>
-__global__ void __launch_bounds__(kThreads) window_attention_tc_kernel(const Params p) {
+__global__ void __launch_bounds__(kThreads, DP <= 32 ? 4 : 3) window_attention_tc_kernel(const Params p) {
   constexpr int kChunks = DP / 8;                         // 16-byte chunks per head slice
   constexpr int kSboQ = kChunks * kLbo + 16;              // +16: stagger 8-row groups across banks
   constexpr int kSboP = (kBlockKeys / 8) * kLbo + 16;
@@ -240,10 +240,19 @@ __global__ void __launch_bounds__(kThreads) window_attention_tc_kernel(const Par
 
     // ---- softmax on this thread's row ----
     // A key at grouped position kp is in this row's window iff qws <= kp < qws + qlen, i.e. the valid keys of the block
-    // are the index range [lo, hi): no mask array in memory.  (Skipping the off-diagonal 16-column groups / 8-key chunks
-    // with warp votes was measured SLOWER -- 26.8 vs 20.8 ms per step -- the kernel is latency-, not ALU-bound.)
+    // are the index range [lo, hi): no mask array in memory.
     const int kb0 = ks + blk * kBlockKeys;
     const int lo = max(qws - kb0, 0), hi = min(qws + qlen - kb0, kBlockKeys);
+    // valid keys as a bit mask: one LOP3 + FSEL per element instead of two compares; the scale and the running maximum
+    // are folded into one FFMA feeding ex2.approx.ftz (masked scores are -inf -> probability exactly 0)
+    const uint64_t valid = hi > lo ? ((~0ull >> (64 - (hi - lo))) << lo) : 0ull;
+    const uint32_t v_lo = (uint32_t)valid, v_hi = (uint32_t)(valid >> 32);
+    uint32_t pk[kBlockKeys / 2];
+    float alpha = 1.0f;
+    // Windows are short, so most (warp, key block) pairs are entirely off the block diagonal: one vote skips the TMEM
+    // load and the whole softmax for them (their P rows are zero).
+    const bool warp_has_keys = __any_sync(0xffffffffu, valid != 0ull);
+    if (warp_has_keys) {
     float s[kBlockKeys];
     {
       uint32_t r[32];
@@ -256,10 +265,6 @@ __global__ void __launch_bounds__(kThreads) window_attention_tc_kernel(const Par
 #pragma unroll
       for (int i = 0; i < 32; ++i) s[32 + i] = __uint_as_float(r[i]);
     }
-    // valid keys as a bit mask: one LOP3 + FSEL per element instead of two compares; the scale and the running maximum
-    // are folded into one FFMA feeding ex2.approx.ftz (masked scores are -inf -> probability exactly 0)
-    const uint64_t valid = hi > lo ? ((~0ull >> (64 - (hi - lo))) << lo) : 0ull;
-    const uint32_t v_lo = (uint32_t)valid, v_hi = (uint32_t)(valid >> 32);
     float m_new = m_run;                                           // maxima are kept in raw (unscaled) score units
 #pragma unroll
     for (int j = 0; j < kBlockKeys; ++j) {
@@ -268,10 +273,9 @@ __global__ void __launch_bounds__(kThreads) window_attention_tc_kernel(const Par
       m_new = fmaxf(m_new, s[j]);
     }
     const float m_use = (m_new == -INFINITY) ? 0.0f : m_new;      // nothing valid so far: ex2(-inf) = 0 everywhere
-    const float alpha = ex2_ftz((m_run - m_use) * scale);          // m_run = -inf -> 0 (l_run, O are still 0 then)
+    alpha = ex2_ftz((m_run - m_use) * scale);          // m_run = -inf -> 0 (l_run, O are still 0 then)
     const float neg_ms = -m_use * scale;
     float l_blk = 0.0f;
-    uint32_t pk[kBlockKeys / 2];
 #pragma unroll
     for (int j = 0; j < kBlockKeys; j += 2) {
       const float a = ex2_ftz(fmaf(s[j], scale, neg_ms)), b = ex2_ftz(fmaf(s[j + 1], scale, neg_ms));
@@ -281,6 +285,10 @@ __global__ void __launch_bounds__(kThreads) window_attention_tc_kernel(const Par
     }
     l_run = l_run * alpha + l_blk;
     m_run = m_new;
+    } else {
+#pragma unroll
+      for (int i = 0; i < kBlockKeys / 2; ++i) pk[i] = 0u;
+    }
 #pragma unroll
     for (int c = 0; c < kBlockKeys / 8; ++c)
       *reinterpret_cast<uint4 *>(p_s + core_off(tid, c, kSboP)) = make_uint4(pk[4 * c], pk[4 * c + 1], pk[4 * c + 2], pk[4 * c + 3]);
