@@ -117,7 +117,8 @@ int os3d_spconv_fwd_f32(const float *in, const int32_t *nbr, int64_t m_out, int 
                         const float *bias, float *out, void *stream);
 /* bf16 in / bf16 out, f32 accumulate in TMEM on the tcgen05 tensor cores.  Fused epilogue: y = acc*scale[c]+shift[c]
  * (bias and folded BatchNorm), optional residual add [m_out, cout] bf16, optional ReLU.  scale/shift (both or neither)
- * and residual may be NULL.  in: rows of `cin` bf16 with cin % 8 == 0 (callers zero-pad); cout % 16 == 0, cout <= 512
+ * and residual may be NULL.  relu is a flag word: bit 0 = ReLU; bit 1 = the residual has 2*cout channels per row and
+ * residual[r, 2c] + residual[r, 2c+1] is added AFTER the ReLU (UpBlock's x_m + channel_reduction(cat)).  in: rows of `cin` bf16 with cin % 8 == 0 (callers zero-pad); cout % 16 == 0, cout <= 512
  * (cout % 32 == 0 above 256).  w: the image written by os3d_pack_weight_bf16(cin_pad = cin). */
 int os3d_spconv_fwd_bf16(const void *in, const int32_t *nbr, int64_t m_out, int cin, int cout, const void *w,
                          const float *scale, const float *shift, const void *residual, int relu, void *out,

@@ -157,7 +157,9 @@ __global__ void __launch_bounds__(kThreads) spconv_tc_kernel(const Params p) {
     const int row = quarter * 32 + lane;
     const bool row_ok = row < rows;
     __nv_bfloat16 *orow = p.out + (row0 + row) * p.cout;
-    const __nv_bfloat16 *rrow = p.residual ? p.residual + (row0 + row) * p.cout : nullptr;
+    const bool pair_sum = (p.relu & 2) != 0;   // residual rows hold 2*cout channels; add r[2c] + r[2c+1] after the ReLU
+    const bool do_relu = (p.relu & 1) != 0;
+    const __nv_bfloat16 *rrow = p.residual ? p.residual + (row0 + row) * p.cout * (pair_sum ? 2 : 1) : nullptr;
     for (int col = (warp >> 2) * 16; col < p.cout; col += 16 * (kProducerWarps / 4)) {
       uint32_t v[16];
       if (it > 0) {
@@ -182,7 +184,7 @@ __global__ void __launch_bounds__(kThreads) spconv_tc_kernel(const Params p) {
             y[4 * q + 3] = fmaf(y[4 * q + 3], sc.w, sh.w);
           }
         }
-        if (rrow) {
+        if (rrow && !pair_sum) {
           const uint4 ra = __ldg(reinterpret_cast<const uint4 *>(rrow + col));
           const uint4 rb = __ldg(reinterpret_cast<const uint4 *>(rrow + col) + 1);
           const uint32_t rw[8] = {ra.x, ra.y, ra.z, ra.w, rb.x, rb.y, rb.z, rb.w};
@@ -192,12 +194,24 @@ __global__ void __launch_bounds__(kThreads) spconv_tc_kernel(const Params p) {
             y[2 * i + 1] += __uint_as_float(rw[i] & 0xffff0000u);
           }
         }
+        if (do_relu) {
+#pragma unroll
+          for (int i = 0; i < 16; ++i) y[i] = fmaxf(y[i], 0.0f);
+        }
+        if (rrow && pair_sum) {      // UpBlock: x_m + channel_reduction(cat)  (pointtransformer.py:89-110)
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const uint4 r4 = __ldg(reinterpret_cast<const uint4 *>(rrow + 2 * col) + q);
+            const uint32_t rw[4] = {r4.x, r4.y, r4.z, r4.w};
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+              y[4 * q + i] += __uint_as_float(rw[i] << 16) + __uint_as_float(rw[i] & 0xffff0000u);
+          }
+        }
         uint32_t o[8];
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
-          float a = y[2 * i], b = y[2 * i + 1];
-          if (p.relu) { a = fmaxf(a, 0.0f); b = fmaxf(b, 0.0f); }
-          const __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+          const __nv_bfloat162 h = __floats2bfloat162_rn(y[2 * i], y[2 * i + 1]);
           o[i] = *reinterpret_cast<const uint32_t *>(&h);
         }
         reinterpret_cast<uint4 *>(orow + col)[0] = make_uint4(o[0], o[1], o[2], o[3]);

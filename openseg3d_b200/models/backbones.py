@@ -98,6 +98,10 @@ class UpBlock(spconv.SparseModule):
     def forward(self, x_bottom, x_lateral):
         x_trans = self.transform(x_lateral)
         x = replace_feature(x_trans, torch.cat([x_bottom.features, x_trans.features], dim=1))
+        if not self.training:        # inference: BN + ReLU + channel_reduction(cat) + add in the bottleneck's epilogue
+            conv, bn = self.bottleneck[0], self.bottleneck[1]
+            scale, shift = bn_scale_shift(bn, conv.bias)
+            return self.out(conv(x, scale=scale, shift=shift, residual=x.features, relu=3))
         x_m = self.bottleneck(x)
         x = self.channel_reduction(x, x_m.features.shape[1])
         x = replace_feature(x, x_m.features + x.features)

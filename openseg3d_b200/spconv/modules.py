@@ -27,7 +27,8 @@ def sparse_conv_forward(features, nbr, weight, bias, packed_cache, scale=None, s
     """out[r] = epilogue( sum_k features[nbr[r, k]] @ W[:, k, :].T ).
 
     fp32 features -> exact FP32-pipe kernel (+ torch epilogue); bf16 features -> tcgen05 kernel with the epilogue
-    (scale/shift = folded bias + BatchNorm, residual, ReLU) fused."""
+    (scale/shift = folded bias + BatchNorm, residual, ReLU) fused.  ``relu`` is the C ABI's flag word: bit 0 = ReLU,
+    bit 1 = ``residual`` has 2*cout channels and residual[:, 2c] + residual[:, 2c+1] is added after the ReLU."""
     _lib.require_cuda(features, nbr)
     features = features.contiguous()
     m_out, cout, cin = nbr.shape[0], weight.shape[0], weight.shape[-1]
@@ -40,9 +41,14 @@ def sparse_conv_forward(features, nbr, weight, bias, packed_cache, scale=None, s
                   work=lambda: 2.0 * cin * cout * int((nbr >= 0).sum().item()))
         if scale is not None:
             out = out * scale + shift
-        if residual is not None:
+        flags = int(relu)
+        if residual is not None and not flags & 2:
             out = out + residual
-        return F.relu_(out) if relu else out
+        if flags & 1:
+            out = F.relu_(out)
+        if residual is not None and flags & 2:       # UpBlock: + channel_reduction(residual) after the ReLU
+            out = out + residual.view(m_out, cout, 2).sum(dim=2)
+        return out
     if features.dtype == torch.bfloat16:
         w, cin_pad = packed_cache.get('bf16', weight)
         if cin_pad != cin:
