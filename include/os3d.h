@@ -115,19 +115,28 @@ int os3d_strided_tables(const int32_t *idx, int64_t m, int sz, int sy, int sx, c
  * replaces: SubMConv3d / SparseConv3d / SparseInverseConv3d forward (spconv-cu113; seg3d/utils/spconv_utils.py:16-22). */
 int os3d_spconv_fwd_f32(const float *in, const int32_t *nbr, int64_t m_out, int cin, int cout, const float *w,
                         const float *bias, float *out, void *stream);
-/* bf16 in / bf16 out, f32 accumulate in TMEM on the tcgen05 tensor cores.  Fused epilogue: y = acc*scale[c]+shift[c]
- * (bias and folded BatchNorm), optional residual add [m_out, cout] bf16, optional ReLU.  scale/shift (both or neither)
- * and residual may be NULL.  relu is a flag word: bit 0 = ReLU; bit 1 = the residual has 2*cout channels per row and
- * residual[r, 2c] + residual[r, 2c+1] is added AFTER the ReLU (UpBlock's x_m + channel_reduction(cat)).  in: rows of `cin` bf16 with cin % 8 == 0 (callers zero-pad); cout % 16 == 0, cout <= 512
- * (cout % 32 == 0 above 256).  w: the image written by os3d_pack_weight_bf16(cin_pad = cin). */
-int os3d_spconv_fwd_bf16(const void *in, const int32_t *nbr, int64_t m_out, int cin, int cout, const void *w,
-                         const float *scale, const float *shift, const void *residual, int relu, void *out,
-                         void *stream);
+/* Tile form of a kernel map for the tensor-core path: nbr [m, 27] -> nbr_t [27][m_pad] (offset-major, m_pad = m rounded
+ * up to 128, padding rows -1) and tile_mask [m_pad / 128] (bit k set when some row of the 128-row tile has a neighbour
+ * at offset k).  Built once per kernel map and shared by every conv that uses the map. */
+int os3d_kernel_map_tiles(const int32_t *nbr, int64_t m, int32_t *nbr_t, uint32_t *tile_mask, void *stream);
+/* bf16 in / bf16 out, f32 accumulate in TMEM on the tcgen05 tensor cores; the gathered operand is fetched by TMA
+ * (cp.async.bulk.tensor tile::gather4) straight into the UMMA shared-memory layout.  Fused epilogue:
+ * y = acc*scale[c]+shift[c] (bias and folded BatchNorm), optional residual add [m_out, cout] bf16, optional ReLU.
+ * scale/shift (both or neither) and residual may be NULL.  flags: bit 0 = ReLU; bit 1 = the residual has 2*cout
+ * channels per row and residual[r, 2c] + residual[r, 2c+1] is added AFTER the ReLU (UpBlock's
+ * x_m + channel_reduction(cat), pointtransformer.py:89-110).
+ * in: [m_in, cin] bf16 rows, 16-byte aligned, cin % 8 == 0 (callers zero-pad); cout % 16 == 0, cout <= 512
+ * (cout % 32 == 0 above 256).  nbr_t / tile_mask: os3d_kernel_map_tiles of the map.  w: os3d_pack_weight_bf16 image.
+ * replaces: SubMConv3d / SparseConv3d / SparseInverseConv3d forward (spconv-cu113; seg3d/utils/spconv_utils.py:16-22)
+ *           and the BatchNorm1d / ReLU / residual add after them (spconv_utils.py:26-30, pointtransformer.py:47-66). */
+int os3d_spconv_fwd_bf16(const void *in, int64_t m_in, const int32_t *nbr_t, const uint32_t *tile_mask, int64_t m_out,
+                         int cin, int cout, const void *w, const float *scale, const float *shift, const void *residual,
+                         int flags, void *out, void *stream);
 /* spconv 2.x weight [cout, kz, ky, kx, cin] f32 -> kernel layouts.  f32: [27, cin, cout].  bf16: the shared-memory image
- * of the UMMA B operand, [ceil(27*cin_pad/64)][cout][128 B swizzled] (os3d_spconv_bf16_packed_elems elements). */
-int os3d_spconv_bf16_packed_elems(int cin_pad, int cout, int64_t *elems);
+ * of the UMMA B operand, [27 * ceil(cin/64)][cout][128 B swizzled] (os3d_spconv_bf16_packed_elems elements). */
+int os3d_spconv_bf16_packed_elems(int cin, int cout, int64_t *elems);
 int os3d_pack_weight_f32(const float *w_spconv, int cin, int cout, float *w_packed, void *stream);
-int os3d_pack_weight_bf16(const float *w_spconv, int cin, int cout, int cin_pad, void *w_packed, void *stream);
+int os3d_pack_weight_bf16(const float *w_spconv, int cin, int cout, void *w_packed, void *stream);
 
 /* ---------------------------------------------------------------- stage 4: window partition + attention --- */
 

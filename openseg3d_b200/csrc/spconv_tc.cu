@@ -2,28 +2,31 @@
 //
 //   out[r, :] = epilogue( sum_k  in[nbr[r, k], :] . W[k] )        bf16 in / bf16 out, fp32 accumulate in TMEM
 //
-// One CTA owns 128 output rows (UMMA M = 128, cta_group::1) and ALL output channels: the accumulator is a
-// [128 lanes x Cout columns] fp32 tile in tensor memory, so a gathered input row is fetched once per CTA and nothing
-// is ever scattered or atomically added.  The contraction dimension is the flattened (offset k, input channel) axis,
-// 27*Cin long, cut into 64-element blocks (one 128-byte SWIZZLE_128B row per output row / output channel):
+// What bounds this op on B200 is the L2 -> SM fabric, not the tensor pipe: every 128-row tile pulls its gathered rows
+// (27 * Cin * 2 B * 128 * fill) AND a full copy of the weights (27 * Cin * Cout * 2 B) out of L2 (ncu of the first
+// one-tile-per-CTA kernel on the L2 192->96 layer: 13.5 GB through the crossbar, 7.9 GB of it weights,
+// profiles/r01b_spconv_l2_192_96_one_tile.txt).  So one CTA owns T consecutive 128-row tiles with T accumulators side
+// by side in tensor memory (T * Cout <= 512 fp32 columns), and a weight K-block staged once in shared memory feeds all
+// T tiles: weight traffic per output row drops T-fold.  The contraction axis is (offset k, channel block of 64).
 //
-//   warps 0-7  producers : gather.  Thread t owns 16-byte chunk (t & 7) of rows (t >> 3) + 32 j; each chunk is one
-//              cp.async (LDGSTS, zero-fill when the row has no neighbour at that offset) straight into the swizzled
-//              K-major UMMA layout; 8 lanes cover one 128-byte row, so every global request is a full line.
-//              Completion is signalled by cp.async.mbarrier.arrive.noinc on the stage's full barrier, so producers never
-//              wait on their own loads (a per-stage fence.proxy.async in the producers costs a MEMBAR that drains the
-//              in-flight LDGSTS: measured 1.5 us per K-block); the proxy fence is executed by the MMA thread instead.
-//              Weights: the packed image is stored in global memory already swizzled, one contiguous [Cout x 128 B]
-//              slab per K-block, so ONE cp.async.bulk (TMA bulk copy, mbarrier complete_tx) by one thread fills B.
-//   warp 8     MMA issuer : one thread issues tcgen05.mma.kind::f16 (4 K-steps x N-parts per block), commits the
-//              stage back to the producers (tcgen05.commit -> empty barrier) and finally signals the epilogue.
-//   warps 0-7  epilogue  : tcgen05.ld 32x32b (lane = output row; warps w and w+4 split the columns), y = acc*scale + shift (+ residual) (ReLU), bf16,
-//              32-byte vector stores.  Bias, eval-mode BatchNorm, the residual add and the ReLU of the reference's
-//              SparseBasicBlock / ConvModule therefore never touch HBM as separate passes.
-//   K-blocks whose offsets have no neighbour anywhere in the tile are skipped by all three roles (same enumeration).
+//   warps 0-7 producers : gather.  Thread t owns 16-byte chunk (t & 7) of rows (t >> 3) + 32 j of a 128-row slot; each
+//            chunk is one cp.async (LDGSTS, zero-fill when the row has no neighbour at that offset) straight into the
+//            SWIZZLE_128B K-major UMMA layout.  Neighbour rows come from the offset-major table ([27][m_pad]) and are
+//            prefetched one offset ahead into registers; each warp keeps 3 slots of copies in flight
+//            (cp.async groups) and signals the oldest with ONE mbarrier arrive per warp.
+//   warp 9  weights  : the
+//            packed image is stored already swizzled, one contiguous [Cout x 128 B] slab per K-block = ONE
+//            cp.async.bulk (TMA bulk copy, mbarrier complete_tx).
+//            (TMA tile::gather4 was built and measured for this gather first: ~40 cycles per 4-row request per SM,
+//            12.8 B/clk/SM, 1.3-1.9x slower than the LDGSTS gather on every layer -- DESIGN.md "Measured dead ends".)
+//   warp 8  MMA      : one thread issues tcgen05.mma.kind::f16 (M = 128, N = Cout, K = 16 per instruction) into the
+//            tile's accumulator; tcgen05.commit frees the A slot / the weight slot.
+//   warps 0-7 epilogue (after their gather loop): tcgen05.ld, y = acc*scale + shift (+ residual) (ReLU)
+//            (+ pair-summed residual), bf16, 32-byte vector stores.
+//   (tile, offset) pairs with no neighbour anywhere in the tile are skipped by all roles (per-tile 27-bit masks).
 //
 // replaces: SubMConv3d / SparseConv3d / SparseInverseConv3d forward of spconv-cu113 (+ the BatchNorm1d / ReLU / add
-// that follow them in seg3d/utils/spconv_utils.py:26-30 and seg3d/models/backbones/pointtransformer.py:47-66).
+// that follow them in seg3d/utils/spconv_utils.py:26-30 and seg3d/models/backbones/pointtransformer.py:47-66,89-110).
 #include "common.cuh"
 #include "tc_ptx.cuh"
 
@@ -34,258 +37,326 @@ using namespace ptx;
 constexpr int kTileM = 128;
 constexpr int kBlockK = 64;                        // bf16 elements per K-block = one 128-byte swizzle row
 constexpr int kATileBytes = kTileM * 128;          // 16 KB
-constexpr int kProducerWarps = 8;                  // gather producers, then epilogue (two warps per TMEM lane quarter)
-constexpr int kProducerThreads = kProducerWarps * 32;
-constexpr int kThreads = kProducerThreads + 32;    // + the MMA-issuing warp
-constexpr int kMaxStages = 6;
+constexpr int kEpiWarps = 8;
+constexpr int kThreads = (kEpiWarps + 2) * 32;     // 8 gather / epilogue warps + the MMA warp + the weight-loader warp
+constexpr int kMaxTiles = 10;                      // accumulators per CTA
+constexpr int kMaxSA = 8, kMaxSB = 4;             // ring depths (A tiles / weight slabs)
 
 struct Params {
-  const __nv_bfloat16 *in;
-  const int32_t *nbr;
-  int64_t m_out;
-  int cin;              // feature row pitch in elements (multiple of 8)
-  int cout;             // multiple of 16, <= 512
-  const __nv_bfloat16 *w_img;
-  const int32_t *chunk_tab;   // [n_blocks * 8]: (offset k << 16) | first channel of the 16-byte chunk, -1 beyond K
-  const uint32_t *blk_mask;   // [n_blocks]: bit mask of the kernel offsets a K-block touches
-  int n_blocks;         // ceil(27 * cin / 64)
-  int chunks_per_offset;  // cin / 8
-  int total_chunks;     // 27 * cin / 8
+  const __nv_bfloat16 *in;    // [m_in, cin] bf16
+  int cin;                    // row pitch in elements (multiple of 8)
+  const int32_t *nbr_t;       // [27][m_pad] offset-major neighbour rows (-1 = none)
+  const uint32_t *tile_mask;  // [m_pad / 128] offsets present in each 128-row tile
+  int64_t m_out, m_pad;
+  int n_tiles;
+  int cin16;                  // cin rounded up to 16 (MMA K granularity; the excess columns are zero on both operands)
+  int cout, ncb;              // ncb = ceil(cin / 64) channel blocks per offset
+  const __nv_bfloat16 *w_img; // [27 * ncb][cout][64] swizzled weight image
   const float *scale, *shift;
   const __nv_bfloat16 *residual;
-  int relu;
+  int flags;
   __nv_bfloat16 *out;
-  int tmem_cols;        // power of two >= cout, >= 32
-  int n_parts;          // 1, or 2 when cout > 256
-  int n_per_part;       // cout / n_parts (multiple of 16)
-  uint32_t idesc;       // tcgen05 instruction descriptor (bf16 x bf16 -> f32, M=128, N=n_per_part, K-major A and B)
-  int stages;
+  int tmem_cols, n_parts, n_per_part;
+  uint32_t idesc;
+  int tiles_per_cta, sa, sb;
+  int sa_log2;
 };
 
-__global__ void __launch_bounds__(kThreads) spconv_tc_kernel(const Params p) {
+__global__ void __launch_bounds__(kThreads, 1) spconv_tc_kernel(const Params p) {
   extern __shared__ uint8_t smem_raw[];
-  // carve: 1024-aligned A stages | B stages | neighbour tile | barriers
   const uint32_t raw = smem_u32(smem_raw);
   const uint32_t base = (raw + 1023u) & ~1023u;
   uint8_t *smem = smem_raw + (base - raw);
-  const int b_tile_bytes = p.cout * 128;
+  const int b_bytes = p.cout * 128;
   const uint32_t a_base = base;
-  const uint32_t b_base = base + p.stages * kATileBytes;
-  uint8_t *tail = smem + p.stages * (kATileBytes + b_tile_bytes);
-  int32_t *nbr_s = reinterpret_cast<int32_t *>(tail);                          // [128][27]
-  uint64_t *bars = reinterpret_cast<uint64_t *>(tail + kTileM * OS3D_KVOL * 4);  // full[S], empty[S], accum
-  uint32_t *misc = reinterpret_cast<uint32_t *>(bars + 2 * kMaxStages + 1);     // [0] tmem base, [1] offset mask
-  const uint32_t full0 = smem_u32(bars), empty0 = smem_u32(bars + kMaxStages), accum_bar = smem_u32(bars + 2 * kMaxStages);
+  const uint32_t b_base = base + p.sa * kATileBytes;
+  uint8_t *tail = smem + p.sa * kATileBytes + p.sb * b_bytes;
+  uint64_t *bars = reinterpret_cast<uint64_t *>(tail);   // a_full[kMaxSA] a_empty[kMaxSA] b_full[kMaxSB] b_empty[kMaxSB] accum
+  uint32_t *misc = reinterpret_cast<uint32_t *>(bars + 2 * kMaxSA + 2 * kMaxSB + 1);   // [0] tmem base, [1..] tile masks
+  const uint32_t a_full = smem_u32(bars), a_empty = smem_u32(bars + kMaxSA);
+  const uint32_t b_full = smem_u32(bars + 2 * kMaxSA), b_empty = smem_u32(bars + 2 * kMaxSA + kMaxSB);
+  const uint32_t accum_bar = smem_u32(bars + 2 * kMaxSA + 2 * kMaxSB);
+  uint32_t *masks_s = misc + 1;
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int64_t row0 = (int64_t)blockIdx.x * kTileM;
-  const int rows = (int)min((int64_t)kTileM, p.m_out - row0);
+  const int tile0 = blockIdx.x * p.tiles_per_cta;
+  const int ntile = min(p.tiles_per_cta, p.n_tiles - tile0);
 
   if (tid == 0) {
-    for (int s = 0; s < p.stages; ++s) {
-      mbar_init(full0 + 8 * s, kProducerThreads + 1);
-      mbar_init(empty0 + 8 * s, 1);
-    }
+    for (int s = 0; s < p.sa; ++s) { mbar_init(a_full + 8 * s, 32); mbar_init(a_empty + 8 * s, 1); }
+    for (int s = 0; s < p.sb; ++s) { mbar_init(b_full + 8 * s, 1); mbar_init(b_empty + 8 * s, 1); }
     mbar_init(accum_bar, 1);
-    misc[1] = 0;
     fence_barrier_init();
   }
+  if (tid < kMaxTiles) masks_s[tid] = tid < ntile ? __ldg(p.tile_mask + tile0 + tid) : 0u;
   __syncthreads();
-  if (warp == kProducerWarps) tmem_alloc(smem_u32(&misc[0]), (uint32_t)p.tmem_cols);
-  {
-    uint32_t mask = 0;
-    for (int t = tid; t < kTileM * OS3D_KVOL; t += kThreads) {
-      const int r = t / OS3D_KVOL;
-      const int32_t v = r < rows ? __ldg(p.nbr + row0 * OS3D_KVOL + t) : -1;
-      nbr_s[t] = v;
-      if (v >= 0) mask |= 1u << (t - r * OS3D_KVOL);
-    }
-    mask = __reduce_or_sync(0xffffffffu, mask);
-    if (lane == 0 && mask) atomicOr(&misc[1], mask);
-  }
+  if (warp == kEpiWarps) tmem_alloc(smem_u32(&misc[0]), (uint32_t)p.tmem_cols);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = misc[0];
-  const uint32_t has_k = misc[1];
+  uint32_t any = 0;
+#pragma unroll
+  for (int t = 0; t < kMaxTiles; ++t) any |= masks_s[t];
 
-  if (warp < kProducerWarps) {
+  if (warp < kEpiWarps) {
     // ================================ producers ================================
-    // Per-thread invariants: chunk c of rows r0 + 16 j.  Everything that does not depend on the K-block is hoisted;
-    // the (offset, channel) of a chunk comes from a per-layer table written next to the weight image, so the loop
-    // body is: table load, then per row { LDS neighbour, multiply-add address, LDGSTS }.
-    constexpr int kRowStep = kProducerThreads / 8, kRowsPerThread = kTileM / kRowStep;
-    const int c = tid & 7, r0 = tid >> 3;
-    const uint32_t dst0 = (uint32_t)(r0 * 128 + ((c ^ (r0 & 7)) << 4));      // row r0 + kRowStep j -> + j * kRowStep * 128
-    const int32_t *nrow = nbr_s + r0 * OS3D_KVOL;                           // row r0 + kRowStep j -> + j * kRowStep * 27
-    const char *in_bytes = reinterpret_cast<const char *>(p.in);
-    const uint32_t row_bytes = (uint32_t)p.cin * 2u;
-    const int32_t *tab = p.chunk_tab + c;
-    int it = 0, stage = 0;
-    uint32_t phase = 1;                                                     // empty barriers start "free"
-    for (int blk = 0; blk < p.n_blocks; ++blk) {
-      if (!(__ldg(p.blk_mask + blk) & has_k)) continue;
-      mbar_wait(empty0 + 8 * stage, phase);
-      if (tid == 0) {
-        mbar_arrive_expect_tx(full0 + 8 * stage, (uint32_t)b_tile_bytes);
-        bulk_g2s(b_base + stage * b_tile_bytes, p.w_img + (int64_t)blk * p.cout * kBlockK, (uint32_t)b_tile_bytes,
-                 full0 + 8 * stage);
-      }
-      const int32_t t = __ldg(tab + blk * 8);
-      const int koff = t >> 16;                        // -1 when the chunk lies beyond 27 * cin (t == -1)
-      const uint32_t ch_bytes = (uint32_t)(t & 0xffff) * 2u;
-      const uint32_t a_dst = a_base + stage * kATileBytes + dst0;
-#pragma unroll
-      for (int j = 0; j < kRowsPerThread; ++j) {
-        const int32_t n = t >= 0 ? nrow[j * kRowStep * OS3D_KVOL + koff] : -1;
-        const char *src = in_bytes + ((uint64_t)((uint32_t)max(n, 0) * row_bytes) + ch_bytes);
-        cp_async_16(a_dst + j * kRowStep * 128, src, n >= 0 ? 16u : 0u);
-      }
-      // asynchronous arrive: fires on the full barrier once this thread's copies above have landed -- the producer
-      // never waits on its own loads and runs ahead until the ring is full
-      cp_async_mbar_arrive_noinc(full0 + 8 * stage);
-      ++it;
-      if (++stage == p.stages) { stage = 0; phase ^= 1; }
-    }
-
-    // ================================ epilogue ================================
-    if (it > 0) {
-      mbar_wait(accum_bar, 0);
-      tc_fence_after();
-    }
-    const int quarter = warp & 3;                       // TMEM lanes [32 q, 32 q + 32) are visible to warps q and q + 4
-    const int row = quarter * 32 + lane;
-    const bool row_ok = row < rows;
-    __nv_bfloat16 *orow = p.out + (row0 + row) * p.cout;
-    const bool pair_sum = (p.relu & 2) != 0;   // residual rows hold 2*cout channels; add r[2c] + r[2c+1] after the ReLU
-    const bool do_relu = (p.relu & 1) != 0;
-    const __nv_bfloat16 *rrow = p.residual ? p.residual + (row0 + row) * p.cout * (pair_sum ? 2 : 1) : nullptr;
-    for (int col = (warp >> 2) * 16; col < p.cout; col += 16 * (kProducerWarps / 4)) {
-      uint32_t v[16];
-      if (it > 0) {
-        tmem_ld16(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)col, v);
-        tmem_ld_wait();
-      } else {
-#pragma unroll
-        for (int i = 0; i < 16; ++i) v[i] = 0u;
-      }
-      if (row_ok) {
-        float y[16];
-#pragma unroll
-        for (int i = 0; i < 16; ++i) y[i] = __uint_as_float(v[i]);
-        if (p.scale) {
-#pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            const float4 sc = __ldg(reinterpret_cast<const float4 *>(p.scale + col) + q);
-            const float4 sh = __ldg(reinterpret_cast<const float4 *>(p.shift + col) + q);
-            y[4 * q + 0] = fmaf(y[4 * q + 0], sc.x, sh.x);
-            y[4 * q + 1] = fmaf(y[4 * q + 1], sc.y, sh.y);
-            y[4 * q + 2] = fmaf(y[4 * q + 2], sc.z, sh.z);
-            y[4 * q + 3] = fmaf(y[4 * q + 3], sc.w, sh.w);
+    // A full / empty mbarrier round trip costs ~300 cycles per thread (tools/bench_mbar.cu), whatever the ring depth:
+    // with all warps cooperating on every slot that was the pace of the whole gather.  So each warp fills WHOLE slots
+    // on its own: slot u of the (offset, channel block, tile) sequence goes to warp u mod n_prod and always lands in
+    // ring slot u mod n_prod, with that slot's own barrier pair.  Lane l owns 16-byte chunk (l & 7) of rows
+    // 32 (l >> 3) + i, i = 0..31: 8 lanes cover one 128-byte row, so each global request is a full line.  The 128
+    // neighbour rows of a slot are ONE coalesced int4 per lane from the offset-major table (prefetched a slot ahead);
+    // the row of iteration i is then a warp shuffle away.  Completion: cp.async.mbarrier.arrive.noinc (32 per slot).
+    if (warp < p.sa) {
+      const uint32_t c = lane & 7, g = lane >> 3;
+      const uint32_t nprod_mask = (uint32_t)p.sa - 1u;
+      const uint32_t slot = (uint32_t)warp;
+      const uint32_t dst_base = a_base + slot * kATileBytes + g * 32 * 128;
+      const uint32_t full_bar = a_full + 8 * slot, empty_bar = a_empty + 8 * slot;
+      const char *in_bytes = reinterpret_cast<const char *>(p.in);
+      const uint32_t row_bytes = (uint32_t)p.cin * 2u;
+      const int32_t *nt = p.nbr_t + (int64_t)tile0 * kTileM + 4 * lane;
+      int ik = 0, icb = 0, it = -1;                          // iterator over the slot sequence
+      uint32_t iu = 0;
+      auto next_mine = [&]() -> bool {
+        while (true) {
+          if (++it >= ntile) { it = 0; if (++icb >= p.ncb) { icb = 0; ++ik; } }
+          if (ik >= OS3D_KVOL) return false;
+          if ((masks_s[it] >> ik) & 1u) {
+            const bool mine = (iu & nprod_mask) == slot;
+            ++iu;
+            if (mine) return true;
           }
         }
-        if (rrow && !pair_sum) {
-          const uint4 ra = __ldg(reinterpret_cast<const uint4 *>(rrow + col));
-          const uint4 rb = __ldg(reinterpret_cast<const uint4 *>(rrow + col) + 1);
-          const uint32_t rw[8] = {ra.x, ra.y, ra.z, ra.w, rb.x, rb.y, rb.z, rb.w};
+      };
+      bool have = next_mine();
+      int4 v = make_int4(-1, -1, -1, -1);
+      if (have) v = __ldg(reinterpret_cast<const int4 *>(nt + (int64_t)ik * p.m_pad + it * kTileM));
+      uint32_t ph = 1;                                     // empty barriers start "free"
+      while (have) {
+        const int4 cur = v;
+        const uint32_t ch = (uint32_t)icb * kBlockK + c * 8;
+        const bool ch_ok = ch < (uint32_t)p.cin;            // channels >= cin of the last channel block: zero-fill
+        const char *src0 = in_bytes + ch * 2u;
+        have = next_mine();
+        if (have) v = __ldg(reinterpret_cast<const int4 *>(nt + (int64_t)ik * p.m_pad + it * kTileM));
+        mbar_wait(empty_bar, ph);
+        ph ^= 1;
 #pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            y[2 * i] += __uint_as_float(rw[i] << 16);
-            y[2 * i + 1] += __uint_as_float(rw[i] & 0xffff0000u);
-          }
+        for (int i = 0; i < 32; ++i) {
+          const int comp = (i & 3) == 0 ? cur.x : (i & 3) == 1 ? cur.y : (i & 3) == 2 ? cur.z : cur.w;
+          const int n = __shfl_sync(0xffffffffu, comp, (lane & 24) + (i >> 2));
+          cp_async_16(dst_base + i * 128 + ((c ^ (uint32_t)(i & 7)) << 4), src0 + (uint64_t)((uint32_t)max(n, 0) * row_bytes),
+                      (ch_ok && n >= 0) ? 16u : 0u);
         }
-        if (do_relu) {
-#pragma unroll
-          for (int i = 0; i < 16; ++i) y[i] = fmaxf(y[i], 0.0f);
-        }
-        if (rrow && pair_sum) {      // UpBlock: x_m + channel_reduction(cat)  (pointtransformer.py:89-110)
-#pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            const uint4 r4 = __ldg(reinterpret_cast<const uint4 *>(rrow + 2 * col) + q);
-            const uint32_t rw[4] = {r4.x, r4.y, r4.z, r4.w};
-#pragma unroll
-            for (int i = 0; i < 4; ++i)
-              y[4 * q + i] += __uint_as_float(rw[i] << 16) + __uint_as_float(rw[i] & 0xffff0000u);
-          }
-        }
-        uint32_t o[8];
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const __nv_bfloat162 h = __floats2bfloat162_rn(y[2 * i], y[2 * i + 1]);
-          o[i] = *reinterpret_cast<const uint32_t *>(&h);
-        }
-        reinterpret_cast<uint4 *>(orow + col)[0] = make_uint4(o[0], o[1], o[2], o[3]);
-        reinterpret_cast<uint4 *>(orow + col)[1] = make_uint4(o[4], o[5], o[6], o[7]);
+        cp_async_mbar_arrive_noinc(full_bar);
       }
     }
-    tc_fence_before();
-  } else {
-    // ================================ MMA issuer ================================
+  } else if (warp == kEpiWarps + 1) {
+    // ================================ weight loader ================================
+    // its own warp, so that waiting for a free weight slot never delays the gather
     if (lane == 0) {
-      int it = 0, stage = 0;
-      uint32_t phase = 0;
-      for (int blk = 0; blk < p.n_blocks; ++blk) {
-        if (!(__ldg(p.blk_mask + blk) & has_k)) continue;
-        mbar_wait(full0 + 8 * stage, phase);
-        fence_proxy_async();   // cp.async (generic-proxy) writes observed through the barrier -> visible to the MMA's async proxy
-        tc_fence_after();
-        const uint32_t a_stage = a_base + stage * kATileBytes;
-        const uint32_t b_stage = b_base + stage * b_tile_bytes;
-#pragma unroll
-        for (int ks = 0; ks < kBlockK / 16; ++ks) {
-          const uint64_t adesc = make_kmajor_sw128_desc(a_stage + ks * 32);
-          for (int part = 0; part < p.n_parts; ++part) {
-            const uint64_t bdesc = make_kmajor_sw128_desc(b_stage + part * p.n_per_part * 128 + ks * 32);
-            umma_bf16(tmem_base + (uint32_t)(part * p.n_per_part), adesc, bdesc, p.idesc, (it > 0 || ks > 0) ? 1u : 0u);
-          }
+      int sb_i = 0;
+      uint32_t b_ph = 1;
+      for (int k = 0; k < OS3D_KVOL; ++k) {
+        if (!((any >> k) & 1u)) continue;
+        for (int cb = 0; cb < p.ncb; ++cb) {
+          mbar_wait(b_empty + 8 * sb_i, b_ph);
+          mbar_arrive_expect_tx(b_full + 8 * sb_i, (uint32_t)b_bytes);
+          bulk_g2s(b_base + sb_i * b_bytes, p.w_img + (int64_t)(k * p.ncb + cb) * p.cout * kBlockK, (uint32_t)b_bytes,
+                   b_full + 8 * sb_i);
+          if (++sb_i == p.sb) { sb_i = 0; b_ph ^= 1; }
         }
-        umma_commit(empty0 + 8 * stage);  // frees the stage once the MMAs above have read it
-        ++it;
-        if (++stage == p.stages) { stage = 0; phase ^= 1; }
       }
-      if (it > 0) umma_commit(accum_bar);  // accumulator complete -> epilogue
     }
     __syncwarp();
-    tc_fence_before();
+  } else {
+    // ================================ MMA issuer ================================
+    // One thread feeds the tensor pipe, so its instruction count per slot IS the pipeline's pace for small N (ncu of
+    // the first version: 130 instructions per slot, tensor pipe 11 % busy, producers blocked on empty slots).  The loop
+    // is therefore stripped to: barrier wait, fence, 1-8 UTCHMMA whose descriptors differ only in their low word, commit.
+    // The WHOLE warp runs this loop on warp-uniform values; only the tcgen05 instructions are under elect.sync.
+    {
+      int sb_i = 0;
+      uint32_t q = 0, b_ph = 0, started = 0, ready = 0;      // q: slots consumed so far
+      const uint32_t sa_mask = (uint32_t)p.sa - 1u, sa_shift = (uint32_t)p.sa_log2;
+      const uint32_t desc_hi = (uint32_t)(make_kmajor_sw128_desc(0) >> 32);
+      const uint32_t a_lo0 = (uint32_t)make_kmajor_sw128_desc(a_base), b_lo0 = (uint32_t)make_kmajor_sw128_desc(b_base);
+      const uint32_t b_step = (uint32_t)b_bytes >> 4, part_lo = (uint32_t)(p.n_per_part * 128) >> 4;
+      const bool two_parts = p.n_parts == 2;
+      const uint32_t idesc = p.idesc, cout = (uint32_t)p.cout, npp = (uint32_t)p.n_per_part;
+      const int last_steps = (p.cin16 - (p.ncb - 1) * kBlockK) >> 4;
+      for (int k = 0; k < OS3D_KVOL; ++k) {
+        if (!((any >> k) & 1u)) continue;
+        uint32_t tiles_k = 0;                              // tiles of this CTA that have offset k
+        for (int t = 0; t < ntile; ++t) tiles_k |= ((masks_s[t] >> k) & 1u) << t;
+        tiles_k = __shfl_sync(0xffffffffu, tiles_k, 0);
+        for (int cb = 0; cb < p.ncb; ++cb) {
+          const int steps = cb + 1 < p.ncb ? kBlockK / 16 : last_steps;
+          mbar_wait(b_full + 8 * sb_i, b_ph);
+          const uint32_t b_lo = b_lo0 + sb_i * b_step;
+          for (uint32_t rem = tiles_k; rem; rem &= rem - 1) {
+            const uint32_t t = __ffs(rem) - 1;
+            const uint32_t slot = q & sa_mask;
+            if (!ready) mbar_wait(a_full + 8 * slot, (q >> sa_shift) & 1u);
+            // probe the NEXT slot's barrier now: its round trip overlaps the MMAs issued below
+            ready = mbar_test(a_full + 8 * ((q + 1) & sa_mask), ((q + 1) >> sa_shift) & 1u);
+            fence_proxy_async();   // LDGSTS (generic proxy) writes observed through the barrier -> visible to the MMA's async proxy
+            tc_fence_after();
+            const uint32_t a_lo = a_lo0 + slot * (kATileBytes >> 4);
+            const uint32_t d = tmem_base + t * cout;
+            const uint32_t acc0 = (started >> t) & 1u;
+            if (elect_one()) {
+              umma_bf16_lo(d, a_lo, b_lo, desc_hi, idesc, acc0);
+              if (two_parts) umma_bf16_lo(d + npp, a_lo, b_lo + part_lo, desc_hi, idesc, acc0);
+#pragma unroll
+              for (int ks = 1; ks < kBlockK / 16; ++ks) {
+                if (ks < steps) {
+                  umma_bf16_lo(d, a_lo + 2 * ks, b_lo + 2 * ks, desc_hi, idesc, 1u);
+                  if (two_parts) umma_bf16_lo(d + npp, a_lo + 2 * ks, b_lo + part_lo + 2 * ks, desc_hi, idesc, 1u);
+                }
+              }
+              umma_commit(a_empty + 8 * slot);
+            }
+            __syncwarp();
+            started |= 1u << t;
+            ++q;
+          }
+          if (elect_one()) umma_commit(b_empty + 8 * sb_i);
+          __syncwarp();
+          if (++sb_i == p.sb) { sb_i = 0; b_ph ^= 1; }
+        }
+      }
+      if (elect_one()) {
+        if (started) umma_commit(accum_bar);
+        else mbar_arrive(accum_bar);
+      }
+    }
+    __syncwarp();
   }
+  if (warp < kEpiWarps) {
+    // ================================ epilogue ================================
+    mbar_wait(accum_bar, 0);
+    tc_fence_after();
+    const int quarter = warp & 3;                       // TMEM lanes [32 q, 32 q + 32) are visible to warps q and q + 4
+    const bool pair_sum = (p.flags & 2) != 0;           // residual rows hold 2*cout channels; add r[2c] + r[2c+1] after the ReLU
+    const bool do_relu = (p.flags & 1) != 0;
+    for (int t = 0; t < ntile; ++t) {
+      const bool has = masks_s[t] != 0u;
+      const int64_t row = (int64_t)(tile0 + t) * kTileM + quarter * 32 + lane;
+      const bool row_ok = row < p.m_out;
+      __nv_bfloat16 *orow = p.out + row * p.cout;
+      const __nv_bfloat16 *rrow = p.residual ? p.residual + row * p.cout * (pair_sum ? 2 : 1) : nullptr;
+      for (int col = (warp >> 2) * 16; col < p.cout; col += 16 * (kEpiWarps / 4)) {
+        uint32_t v[16];
+        if (has) {
+          tmem_ld16(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(t * p.cout + col), v);
+          tmem_ld_wait();
+        } else {
+#pragma unroll
+          for (int i = 0; i < 16; ++i) v[i] = 0u;
+        }
+        if (row_ok) {
+          float y[16];
+#pragma unroll
+          for (int i = 0; i < 16; ++i) y[i] = __uint_as_float(v[i]);
+          if (p.scale) {
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              const float4 sc = __ldg(reinterpret_cast<const float4 *>(p.scale + col) + q);
+              const float4 sh = __ldg(reinterpret_cast<const float4 *>(p.shift + col) + q);
+              y[4 * q + 0] = fmaf(y[4 * q + 0], sc.x, sh.x);
+              y[4 * q + 1] = fmaf(y[4 * q + 1], sc.y, sh.y);
+              y[4 * q + 2] = fmaf(y[4 * q + 2], sc.z, sh.z);
+              y[4 * q + 3] = fmaf(y[4 * q + 3], sc.w, sh.w);
+            }
+          }
+          if (rrow && !pair_sum) {
+            const uint4 ra = __ldg(reinterpret_cast<const uint4 *>(rrow + col));
+            const uint4 rb = __ldg(reinterpret_cast<const uint4 *>(rrow + col) + 1);
+            const uint32_t rw[8] = {ra.x, ra.y, ra.z, ra.w, rb.x, rb.y, rb.z, rb.w};
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              y[2 * i] += __uint_as_float(rw[i] << 16);
+              y[2 * i + 1] += __uint_as_float(rw[i] & 0xffff0000u);
+            }
+          }
+          if (do_relu) {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) y[i] = fmaxf(y[i], 0.0f);
+          }
+          if (rrow && pair_sum) {      // UpBlock: x_m + channel_reduction(cat)  (pointtransformer.py:89-110)
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              const uint4 r4 = __ldg(reinterpret_cast<const uint4 *>(rrow + 2 * col) + q);
+              const uint32_t rw[4] = {r4.x, r4.y, r4.z, r4.w};
+#pragma unroll
+              for (int i = 0; i < 4; ++i)
+                y[4 * q + i] += __uint_as_float(rw[i] << 16) + __uint_as_float(rw[i] & 0xffff0000u);
+            }
+          }
+          uint32_t o[8];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const __nv_bfloat162 h = __floats2bfloat162_rn(y[2 * i], y[2 * i + 1]);
+            o[i] = *reinterpret_cast<const uint32_t *>(&h);
+          }
+          reinterpret_cast<uint4 *>(orow + col)[0] = make_uint4(o[0], o[1], o[2], o[3]);
+          reinterpret_cast<uint4 *>(orow + col)[1] = make_uint4(o[4], o[5], o[6], o[7]);
+        }
+      }
+    }
+  }
+  tc_fence_before();
   __syncthreads();
-  if (warp == kProducerWarps) {
+  if (warp == kEpiWarps) {
     tc_fence_after();
     tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols);
   }
 }
 
-// spconv 2.x weight [cout, 27, cin] f32  ->  bf16 UMMA image [n_blocks][cout][8 chunks, XOR-swizzled by row & 7][8]:
-// exactly the bytes a K-block's B tile occupies in shared memory, so one bulk copy loads it.  Two small per-layer
-// tables follow the image: chunk_tab[n_blocks * 8] and blk_mask[n_blocks] (see Params).
-__global__ void pack_weight_img_kernel(const float *__restrict__ src, int cin, int cout, int cin_pad, int n_blocks,
-                                       __nv_bfloat16 *__restrict__ dst, int32_t *__restrict__ chunk_tab,
-                                       uint32_t *__restrict__ blk_mask) {
+// [m, 27] row-major kernel map -> offset-major [27][m_pad] (m_pad = 128 * n_tiles, padding rows -1) + per-tile masks.
+__global__ void __launch_bounds__(256) kernel_map_tiles_kernel(const int32_t *__restrict__ nbr, int64_t m, int64_t m_pad,
+                                                               int32_t *__restrict__ nbr_t,
+                                                               uint32_t *__restrict__ tile_mask) {
+  __shared__ int32_t s[kTileM * OS3D_KVOL];
+  __shared__ uint32_t msk;
+  const int64_t row0 = (int64_t)blockIdx.x * kTileM;
+  if (threadIdx.x == 0) msk = 0;
+  __syncthreads();
+  uint32_t mask = 0;
+  for (int t = threadIdx.x; t < kTileM * OS3D_KVOL; t += 256) {
+    const int r = t / OS3D_KVOL;
+    const int32_t v = row0 + r < m ? __ldg(nbr + row0 * OS3D_KVOL + t) : -1;
+    s[t] = v;
+    if (v >= 0) mask |= 1u << (t - r * OS3D_KVOL);
+  }
+  mask = __reduce_or_sync(0xffffffffu, mask);
+  if ((threadIdx.x & 31) == 0 && mask) atomicOr(&msk, mask);
+  __syncthreads();
+  for (int t = threadIdx.x; t < kTileM * OS3D_KVOL; t += 256) {
+    const int k = t >> 7, r = t & 127;
+    nbr_t[(int64_t)k * m_pad + row0 + r] = s[r * OS3D_KVOL + k];
+  }
+  if (threadIdx.x == 0) tile_mask[blockIdx.x] = msk;
+}
+
+// spconv 2.x weight [cout, 27, cin] f32 -> bf16 UMMA image [27 * ncb][cout][8 chunks, XOR-swizzled by row & 7][8]:
+// exactly the bytes a weight K-block occupies in shared memory, so one bulk copy loads it.  K-blocks never straddle
+// kernel offsets (the last channel block of an offset is zero-padded to 64).
+__global__ void pack_weight_img_kernel(const float *__restrict__ src, int cin, int cout, int ncb,
+                                       __nv_bfloat16 *__restrict__ dst) {
   const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  const int64_t total = (int64_t)n_blocks * cout * kBlockK;
-  const int cpo = cin_pad / 8;
-  const int total_chunks = OS3D_KVOL * cpo;
-  if (t < n_blocks * 8) {
-    const int g = (int)t;
-    chunk_tab[g] = g < total_chunks ? (((g / cpo) << 16) | ((g % cpo) * 8)) : -1;
-  }
-  if (t < n_blocks) {
-    const int first = ((int)t * 8) / cpo, last = min((int)t * 8 + 7, total_chunks - 1) / cpo;
-    blk_mask[t] = (uint32_t)(((1ull << (last + 1)) - 1) & ~((1ull << first) - 1));
-  }
+  const int64_t total = (int64_t)OS3D_KVOL * ncb * cout * kBlockK;
   if (t >= total) return;
   const int e = (int)(t & 7);
   const int pc = (int)((t >> 3) & 7);
   const int n = (int)((t >> 6) % cout);
   const int blk = (int)((t >> 6) / cout);
   const int c = pc ^ (n & 7);  // logical chunk stored at physical chunk pc
-  const int g = blk * 8 + c;
-  float v = 0.0f;
-  if (g < total_chunks) {
-    const int koff = g / cpo, ch = (g - koff * cpo) * 8 + e;
-    if (ch < cin) v = src[((int64_t)n * OS3D_KVOL + koff) * cin + ch];
-  }
-  dst[t] = __float2bfloat16(v);
+  const int k = blk / ncb, ch = (blk - k * ncb) * kBlockK + c * 8 + e;
+  dst[t] = __float2bfloat16(ch < cin ? src[((int64_t)n * OS3D_KVOL + k) * cin + ch] : 0.0f);
 }
 
 }  // namespace tc
@@ -293,72 +364,88 @@ __global__ void pack_weight_img_kernel(const float *__restrict__ src, int cin, i
 
 using namespace os3d;
 
-extern "C" int os3d_spconv_bf16_packed_elems(int cin_pad, int cout, int64_t *elems) {
-  if (cin_pad <= 0 || cin_pad % 8 || cout <= 0) return OS3D_ERR_BAD_ARG;
-  const int64_t n_blocks = cdiv((int64_t)OS3D_KVOL * cin_pad, tc::kBlockK);
-  *elems = n_blocks * cout * tc::kBlockK + (n_blocks * 9 * 4 + 64) / 2;   // image + chunk_tab + blk_mask (bf16 units)
-  return 0;
-}
-
-extern "C" int os3d_pack_weight_bf16(const float *w_spconv, int cin, int cout, int cin_pad, void *w_packed,
-                                     void *stream) {
-  if (cin_pad % 8 || cin_pad < cin) return OS3D_ERR_BAD_ARG;
-  const int n_blocks = (int)cdiv((int64_t)OS3D_KVOL * cin_pad, tc::kBlockK);
-  const int64_t total = (int64_t)n_blocks * cout * tc::kBlockK;
-  __nv_bfloat16 *img = (__nv_bfloat16 *)w_packed;
-  int32_t *tab = reinterpret_cast<int32_t *>(img + total);               // total * 2 bytes is a multiple of 128
-  tc::pack_weight_img_kernel<<<(unsigned)cdiv(total, 256), 256, 0, (cudaStream_t)stream>>>(
-      w_spconv, cin, cout, cin_pad, n_blocks, img, tab, reinterpret_cast<uint32_t *>(tab + n_blocks * 8));
+extern "C" int os3d_kernel_map_tiles(const int32_t *nbr, int64_t m, int32_t *nbr_t, uint32_t *tile_mask, void *stream) {
+  if (m < 0) return OS3D_ERR_BAD_ARG;
+  if (m == 0) return 0;
+  const int64_t n_tiles = cdiv(m, tc::kTileM);
+  tc::kernel_map_tiles_kernel<<<(unsigned)n_tiles, 256, 0, (cudaStream_t)stream>>>(nbr, m, n_tiles * tc::kTileM, nbr_t,
+                                                                                   tile_mask);
   OS3D_LAUNCH_CHECK();
   return 0;
 }
 
-extern "C" int os3d_spconv_fwd_bf16(const void *in, const int32_t *nbr, int64_t m_out, int cin, int cout, const void *w,
-                                    const float *scale, const float *shift, const void *residual, int relu, void *out,
-                                    void *stream) {
+extern "C" int os3d_spconv_bf16_packed_elems(int cin, int cout, int64_t *elems) {
+  if (cin <= 0 || cin % 8 || cout <= 0) return OS3D_ERR_BAD_ARG;
+  *elems = (int64_t)OS3D_KVOL * cdiv(cin, tc::kBlockK) * cout * tc::kBlockK;
+  return 0;
+}
+
+extern "C" int os3d_pack_weight_bf16(const float *w_spconv, int cin, int cout, void *w_packed, void *stream) {
+  if (cin <= 0 || cout <= 0) return OS3D_ERR_BAD_ARG;
+  const int ncb = (int)cdiv(cin, tc::kBlockK);
+  const int64_t total = (int64_t)OS3D_KVOL * ncb * cout * tc::kBlockK;
+  tc::pack_weight_img_kernel<<<(unsigned)cdiv(total, 256), 256, 0, (cudaStream_t)stream>>>(
+      w_spconv, cin, cout, ncb, (__nv_bfloat16 *)w_packed);
+  OS3D_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int os3d_spconv_fwd_bf16(const void *in, int64_t m_in, const int32_t *nbr_t, const uint32_t *tile_mask,
+                                    int64_t m_out, int cin, int cout, const void *w, const float *scale,
+                                    const float *shift, const void *residual, int flags, void *out, void *stream) {
   if (cin <= 0 || cin % 8 || cout < 16 || cout % 16 || cout > 512 || (cout > 256 && cout % 32) ||
-      ((scale == nullptr) != (shift == nullptr)))
+      ((scale == nullptr) != (shift == nullptr)) || m_in <= 0 || ((uintptr_t)in & 15))
     return OS3D_ERR_BAD_ARG;
   if (m_out == 0) return 0;
   tc::Params p;
   p.in = (const __nv_bfloat16 *)in;
-  p.nbr = nbr;
-  p.m_out = m_out;
   p.cin = cin;
+  p.nbr_t = nbr_t;
+  p.tile_mask = tile_mask;
+  p.m_out = m_out;
+  p.n_tiles = (int)cdiv(m_out, tc::kTileM);
+  p.m_pad = (int64_t)p.n_tiles * tc::kTileM;
+  p.cin16 = (cin + 15) / 16 * 16;
   p.cout = cout;
+  p.ncb = (int)cdiv(cin, tc::kBlockK);
   p.w_img = (const __nv_bfloat16 *)w;
-  p.n_blocks = (int)cdiv((int64_t)OS3D_KVOL * cin, tc::kBlockK);
-  p.chunk_tab = reinterpret_cast<const int32_t *>(p.w_img + (int64_t)p.n_blocks * cout * tc::kBlockK);
-  p.blk_mask = reinterpret_cast<const uint32_t *>(p.chunk_tab + p.n_blocks * 8);
-  p.chunks_per_offset = cin / 8;
-  p.total_chunks = OS3D_KVOL * cin / 8;
   p.scale = scale;
   p.shift = shift;
   p.residual = (const __nv_bfloat16 *)residual;
-  p.relu = relu;
+  p.flags = flags;
   p.out = (__nv_bfloat16 *)out;
-  int cols = 32;
-  while (cols < cout) cols <<= 1;
-  p.tmem_cols = cols;
   p.n_parts = cout > 256 ? 2 : 1;
   p.n_per_part = cout / p.n_parts;
-  // cute::UMMA::InstrDescriptor: c_format F32 (1<<4), a/b format BF16 (1<<7, 1<<10), K-major A and B, N>>3 at bit 17,
-  // M>>4 at bit 24
-  p.idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.n_per_part >> 3) << 17) | ((uint32_t)(tc::kTileM >> 4) << 24);
-  const int stage_bytes = tc::kATileBytes + cout * 128;
-  const int tail = tc::kTileM * OS3D_KVOL * 4 + (2 * tc::kMaxStages + 1) * 8 + 64;
-  // small tiles: 4 stages so two CTAs share an SM; large tiles: as many stages as fit one CTA per SM
-  int stages = cout <= 48 ? 4 : cout <= 96 ? 3 : (227 * 1024 - 1024 - tail) / stage_bytes;
-  stages = stages > tc::kMaxStages ? tc::kMaxStages : stages;
-  if (stages < 2) return OS3D_ERR_BAD_ARG;
-  p.stages = stages;
-  const int smem = 1024 + stages * stage_bytes + tail;
-  static int configured = 0;
-  if (configured < smem) {
+  p.idesc = ptx::make_idesc_bf16(tc::kTileM, p.n_per_part);
+  // T accumulators per CTA: as many as tensor memory holds, but keep at least ~2 waves of CTAs on the 148 SMs
+  int tiles = 512 / cout;
+  tiles = tiles > tc::kMaxTiles ? tc::kMaxTiles : tiles;
+  while (tiles > 1 && cdiv(p.n_tiles, tiles) < 2 * 148) --tiles;
+  const char *env_t = getenv("OS3D_SPCONV_TILES");   // tuning / test override of the accumulators per CTA
+  if (env_t && atoi(env_t) > 0) tiles = min(atoi(env_t), min(512 / cout, tc::kMaxTiles));
+  p.tiles_per_cta = tiles;
+  int cols = 32;
+  while (cols < tiles * cout) cols <<= 1;
+  p.tmem_cols = cols;
+  const int b_bytes = cout * 128;
+  const int tail = (2 * tc::kMaxSA + 2 * tc::kMaxSB + 1) * 8 + (1 + tc::kMaxTiles) * 4 + 64;
+  const int budget = 227 * 1024 - 1024 - tail;
+  int sb = b_bytes * 3 <= budget / 2 ? 3 : 2;
+  int sa = (budget - sb * b_bytes) / tc::kATileBytes;
+  int sa_log2 = 3;                                           // ring depth: a power of two (index / phase from one counter)
+  while (sa_log2 > 1 && (1 << sa_log2) > sa) --sa_log2;
+  sa = 1 << sa_log2;
+  if ((budget - sb * b_bytes) < sa * tc::kATileBytes) return OS3D_ERR_BAD_ARG;
+  p.sa = sa;
+  p.sa_log2 = sa_log2;
+  p.sb = sb;
+  const int smem = 1024 + sa * tc::kATileBytes + sb * b_bytes + tail;
+  static bool configured = false;
+  if (!configured) {
     OS3D_CUDA(cudaFuncSetAttribute(tc::spconv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    configured = 227 * 1024;
+    configured = true;
   }
-  tc::spconv_tc_kernel<<<(unsigned)cdiv(m_out, tc::kTileM), tc::kThreads, smem, (cudaStream_t)stream>>>(p);
+  tc::spconv_tc_kernel<<<(unsigned)cdiv(p.n_tiles, tiles), tc::kThreads, smem, (cudaStream_t)stream>>>(p);
   OS3D_LAUNCH_CHECK();
   return 0;
 }

@@ -56,11 +56,28 @@ def sparse_conv_forward(features, nbr, weight, bias, packed_cache, scale=None, s
         if scale is None and bias is not None:
             scale, shift = torch.ones_like(bias, dtype=torch.float32), bias.float()
         out = torch.empty((m_out, cout), dtype=torch.bfloat16, device=features.device)
-        _lib.call('os3d_spconv_fwd_bf16', features, nbr, m_out, cin_pad, cout, w, scale, shift,
-                  residual.contiguous() if residual is not None else None, int(relu), out,
+        if m_out == 0 or features.shape[0] == 0:
+            return out.zero_()
+        nbr_t, tile_mask = kernel_map_tiles(nbr)
+        _lib.call('os3d_spconv_fwd_bf16', features, features.shape[0], nbr_t, tile_mask, m_out, cin_pad, cout, w, scale,
+                  shift, residual.contiguous() if residual is not None else None, int(relu), out,
                   work=lambda: 2.0 * cin * cout * int((nbr >= 0).sum().item()))
         return out
     raise RuntimeError(f'sparse conv: unsupported feature dtype {features.dtype}')
+
+
+def kernel_map_tiles(nbr):
+    """(nbr_t [27, m_pad], tile_mask [m_pad / 128]) of a kernel map, built on first use and kept on the map tensor so
+    every conv sharing the map (same ``indice_key``) reuses it."""
+    hit = getattr(nbr, '_os3d_tiles', None)
+    if hit is None:
+        m = nbr.shape[0]
+        n_tiles = (m + 127) // 128
+        nbr_t = torch.empty((27, n_tiles * 128), dtype=torch.int32, device=nbr.device)
+        tile_mask = torch.empty(n_tiles, dtype=torch.int32, device=nbr.device)
+        _lib.call('os3d_kernel_map_tiles', nbr, m, nbr_t, tile_mask)
+        hit = nbr._os3d_tiles = (nbr_t, tile_mask)
+    return hit
 
 
 class _PackedWeights(object):
@@ -86,7 +103,7 @@ class _PackedWeights(object):
             elems = ctypes.c_int64(0)
             _lib.lib().os3d_spconv_bf16_packed_elems(cin_pad, cout, ctypes.byref(elems))
             packed = torch.empty(elems.value, dtype=torch.bfloat16, device=weight.device)
-            _lib.call('os3d_pack_weight_bf16', w32, cin, cout, cin_pad, packed)
+            _lib.call('os3d_pack_weight_bf16', w32, cin, cout, packed)
             val = (packed, cin_pad)
         self._store[kind] = (tag, val)
         return val

@@ -1,5 +1,6 @@
 """Run the bf16 tensor-core sparse conv on real kernel maps (8 synthetic frames) for profiling:
-    python tools/run_spconv.py LEVEL CIN COUT [reps]      LEVEL in 1..4 (submanifold map of that level)
+    python tools/run_spconv.py LEVEL CIN COUT [reps] [flags]      LEVEL in 1..4 (submanifold map of that level);
+    flags: 1 = ReLU, 3 = ReLU + pair-summed residual of 2*COUT channels (the UpBlock bottleneck)
 """
 import os
 import sys
@@ -15,6 +16,7 @@ from openseg3d_b200.spconv.modules import sparse_conv_forward, _PackedWeights  #
 def main():
     level, cin, cout = int(sys.argv[1]), int(sys.argv[2]), int(sys.argv[3])
     reps = int(sys.argv[4]) if len(sys.argv) > 4 else 3
+    flags = int(sys.argv[5]) if len(sys.argv) > 5 else 1
     frames = 8
     pts, _ = synthetic.make_batch(list(range(frames)), 1, False)
     coors, _ = voxelize_batch(torch.from_numpy(pts).cuda(), [0.1, 0.1, 0.1], [-72, -72, -2, 72, 72, 4.4])
@@ -29,12 +31,13 @@ def main():
     cache = _PackedWeights()
     scale, shift = torch.ones(cout, device='cuda'), torch.zeros(cout, device='cuda')
     pairs = int((rb.nbr >= 0).sum().item())
+    res = torch.randn(m, 2 * cout, device='cuda').bfloat16() if flags & 2 else None
     for _ in range(2):
-        sparse_conv_forward(feats, rb.nbr, w, None, cache, scale, shift, None, True)
+        sparse_conv_forward(feats, rb.nbr, w, None, cache, scale, shift, res, flags)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for _ in range(reps):
-        sparse_conv_forward(feats, rb.nbr, w, None, cache, scale, shift, None, True)
+        sparse_conv_forward(feats, rb.nbr, w, None, cache, scale, shift, res, flags)
     e1.record()
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / reps
