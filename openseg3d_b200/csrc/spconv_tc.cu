@@ -62,7 +62,7 @@ struct Params {
   int sa_log2;
 };
 
-__global__ void __launch_bounds__(kThreads, 1) spconv_tc_kernel(const Params p) {
+__global__ void __launch_bounds__(kThreads, 2) spconv_tc_kernel(const Params p) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
   const uint32_t base = (raw + 1023u) & ~1023u;
@@ -117,30 +117,46 @@ __global__ void __launch_bounds__(kThreads, 1) spconv_tc_kernel(const Params p) 
       const char *in_bytes = reinterpret_cast<const char *>(p.in);
       const uint32_t row_bytes = (uint32_t)p.cin * 2u;
       const int32_t *nt = p.nbr_t + (int64_t)tile0 * kTileM + 4 * lane;
-      int ik = 0, icb = 0, it = -1;                          // iterator over the slot sequence
-      uint32_t iu = 0;
+      // Iterator over this warp's slots.  Per (offset, channel block) the CTA's slots are the set bits of tiles_k in
+      // ascending tile order; the warp owns those whose running index is congruent to its ring slot.
+      int ik = -1, icb = p.ncb - 1, it = 0;                  // the first advance moves to offset 0, block 0
+      uint32_t u0 = 0, tiles_k = 0, cnt = 0, r = 0;           // u0: slots before this (k, cb); r: my next rank in it
       auto next_mine = [&]() -> bool {
         while (true) {
-          if (++it >= ntile) { it = 0; if (++icb >= p.ncb) { icb = 0; ++ik; } }
-          if (ik >= OS3D_KVOL) return false;
-          if ((masks_s[it] >> ik) & 1u) {
-            const bool mine = (iu & nprod_mask) == slot;
-            ++iu;
-            if (mine) return true;
+          if (r < cnt) {
+            it = __fns(tiles_k, 0, r + 1);
+            r += nprod_mask + 1;
+            return true;
           }
+          u0 += cnt;
+          if (++icb >= p.ncb) {
+            icb = 0;
+            do {
+              if (++ik >= OS3D_KVOL) return false;
+            } while (!((any >> ik) & 1u));
+            tiles_k = 0;
+            for (int t = 0; t < ntile; ++t) tiles_k |= ((masks_s[t] >> ik) & 1u) << t;
+            cnt = __popc(tiles_k);
+          }
+          r = (slot - u0) & nprod_mask;
         }
       };
-      bool have = next_mine();
-      int4 v = make_int4(-1, -1, -1, -1);
-      if (have) v = __ldg(reinterpret_cast<const int4 *>(nt + (int64_t)ik * p.m_pad + it * kTileM));
+      // neighbour rows are prefetched TWO slots ahead: one slot's work is shorter than a trip to L2 / HBM for the table
+      int4 v0 = make_int4(-1, -1, -1, -1), v1 = v0;
+      int cb0 = 0, cb1 = 0;
+      bool have0 = next_mine();
+      if (have0) { cb0 = icb; v0 = __ldg(reinterpret_cast<const int4 *>(nt + (int64_t)ik * p.m_pad + it * kTileM)); }
+      bool have1 = have0 && next_mine();
+      if (have1) { cb1 = icb; v1 = __ldg(reinterpret_cast<const int4 *>(nt + (int64_t)ik * p.m_pad + it * kTileM)); }
       uint32_t ph = 1;                                     // empty barriers start "free"
-      while (have) {
-        const int4 cur = v;
-        const uint32_t ch = (uint32_t)icb * kBlockK + c * 8;
+      while (have0) {
+        const int4 cur = v0;
+        const uint32_t ch = (uint32_t)cb0 * kBlockK + c * 8;
         const bool ch_ok = ch < (uint32_t)p.cin;            // channels >= cin of the last channel block: zero-fill
         const char *src0 = in_bytes + ch * 2u;
-        have = next_mine();
-        if (have) v = __ldg(reinterpret_cast<const int4 *>(nt + (int64_t)ik * p.m_pad + it * kTileM));
+        have0 = have1; v0 = v1; cb0 = cb1;
+        have1 = have1 && next_mine();
+        if (have1) { cb1 = icb; v1 = __ldg(reinterpret_cast<const int4 *>(nt + (int64_t)ik * p.m_pad + it * kTileM)); }
         mbar_wait(empty_bar, ph);
         ph ^= 1;
 #pragma unroll
@@ -417,25 +433,31 @@ extern "C" int os3d_spconv_fwd_bf16(const void *in, int64_t m_in, const int32_t 
   p.n_parts = cout > 256 ? 2 : 1;
   p.n_per_part = cout / p.n_parts;
   p.idesc = ptx::make_idesc_bf16(tc::kTileM, p.n_per_part);
-  // T accumulators per CTA: as many as tensor memory holds, but keep at least ~2 waves of CTAs on the 148 SMs
-  int tiles = 512 / cout;
-  tiles = tiles > tc::kMaxTiles ? tc::kMaxTiles : tiles;
-  while (tiles > 1 && cdiv(p.n_tiles, tiles) < 2 * 148) --tiles;
-  const char *env_t = getenv("OS3D_SPCONV_TILES");   // tuning / test override of the accumulators per CTA
-  if (env_t && atoi(env_t) > 0) tiles = min(atoi(env_t), min(512 / cout, tc::kMaxTiles));
+  // Occupancy first: what paces this kernel for small Cout is the serial work of ONE MMA-issuing warp per CTA
+  // (barrier round trips, proxy fence, issue), so two or three co-resident CTAs beat one CTA with a deep ring
+  // (measured sweep: gpurun_out/sweep_cfg.log).  Per CTA: T accumulators (T * Cout <= 512 / ctas TMEM
+  // columns), a weight ring of sb slabs and an A ring of sa (power of two) 16 KB slots within 227 KB / ctas.
+  const int ctas = cout <= 256 ? 2 : 1;
+  int tiles = (512 / ctas) / cout;
+  tiles = tiles > 5 ? 5 : tiles < 1 ? 1 : tiles;
+  while (tiles > 1 && cdiv(p.n_tiles, tiles) < 2 * 148 * ctas) --tiles;
+  { const char *e = getenv("OS3D_SPCONV_TILES");   // tuning / test override of the accumulators per CTA
+    if (e && atoi(e) > 0) tiles = min(atoi(e), min(512 / cout, tc::kMaxTiles)); }
   p.tiles_per_cta = tiles;
   int cols = 32;
   while (cols < tiles * cout) cols <<= 1;
   p.tmem_cols = cols;
   const int b_bytes = cout * 128;
   const int tail = (2 * tc::kMaxSA + 2 * tc::kMaxSB + 1) * 8 + (1 + tc::kMaxTiles) * 4 + 64;
-  const int budget = 227 * 1024 - 1024 - tail;
-  int sb = b_bytes * 3 <= budget / 2 ? 3 : 2;
+  const int budget = (227 * 1024) / ctas - 1024 - tail - (ctas > 1 ? 1024 : 0);   // 1 KB per CTA is reserved by the driver
+  int sb = 3;
+  while (sb > 2 && budget - sb * b_bytes < 2 * tc::kATileBytes) --sb;
   int sa = (budget - sb * b_bytes) / tc::kATileBytes;
+  { const char *e = getenv("OS3D_SPCONV_SA"); if (e && atoi(e) > 0 && atoi(e) < sa) sa = atoi(e); }
   int sa_log2 = 3;                                           // ring depth: a power of two (index / phase from one counter)
-  while (sa_log2 > 1 && (1 << sa_log2) > sa) --sa_log2;
+  while (sa_log2 > 0 && (1 << sa_log2) > sa) --sa_log2;
   sa = 1 << sa_log2;
-  if ((budget - sb * b_bytes) < sa * tc::kATileBytes) return OS3D_ERR_BAD_ARG;
+  if (sa < 2 || (budget - sb * b_bytes) < sa * tc::kATileBytes) return OS3D_ERR_BAD_ARG;
   p.sa = sa;
   p.sa_log2 = sa_log2;
   p.sb = sb;
