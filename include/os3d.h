@@ -138,6 +138,21 @@ int os3d_spconv_bf16_packed_elems(int cin, int cout, int64_t *elems);
 int os3d_pack_weight_f32(const float *w_spconv, int cin, int cout, float *w_packed, void *stream);
 int os3d_pack_weight_bf16(const float *w_spconv, int cin, int cout, void *w_packed, void *stream);
 
+/* Linear layer on the same tensor-core kernel (the identity kernel map with one offset), with the epilogues the
+ * SWFormer encoder layer needs fused in:  out[r, :n] = epi( x[r, :k] . W^T + bias )
+ *   flags bit 0 ReLU; bit 2 exact (erf) GELU; bit 3 out = residual + LayerNorm_n(y) * ln_gamma + ln_beta;
+ *   bit 4 y[r, c] += table[tab_idx[r], c] for c < tab_cols (the position-embedding term of q = k = (x + pos) W^T:
+ *   pos W^T is a [window volume, n] table).
+ * x: [m, k] bf16 (k % 8 == 0), w: os3d_pack_linear_bf16 image of the nn.Linear weight [n, k] f32, bias [n] f32 or NULL,
+ * n % 16 == 0, n <= 512; out rows have pitch ldo >= n elements.  residual [m, n] bf16, table [*, tab_cols] bf16.
+ * replaces: the nn.Linear / GELU / LayerNorm / residual chain of EncoderLayer.forward and cosine_multi_head_attention_forward's
+ *           projections (seg3d/models/layers/point_transformer_layer.py:260-298, seg3d/models/layers/cosine_msa.py:48-63,403). */
+int os3d_linear_bf16_packed_elems(int k, int n, int64_t *elems);
+int os3d_pack_linear_bf16(const float *w, int k, int n, void *w_packed, void *stream);
+int os3d_linear_bf16(const void *x, int64_t m, int k, int n, const void *w, const float *bias, int flags,
+                     const void *residual, const float *ln_gamma, const float *ln_beta, float ln_eps, const void *table,
+                     const int32_t *tab_idx, int tab_cols, void *out, int64_t ldo, void *stream);
+
 /* ---------------------------------------------------------------- stage 4: window partition + attention --- */
 
 #define OS3D_MAX_LEVELS 4
@@ -184,6 +199,11 @@ int os3d_group_partition(const int64_t *group, int64_t n, int64_t n_groups, cons
  * replaces: SparseWindowPartitionLayer.get_pos_embed (point_transformer_layer.py:152-207). */
 int os3d_pos_embed(const int32_t *in_win, int64_t m, int c, int win_x, int win_y, int win_z, float temperature,
                    int elem_size, void *out, void *stream);
+/* out[r, :] = x[r, :] + table[idx[r], :] (f32 or bf16 by elem_size, c % 8 == 0): q = k = x + pos with the position
+ * embedding as a [window volume, c] table indexed by the in-window position.
+ * replaces: the flat2window'ed pos-embed add of WindowAttention.forward (point_transformer_layer.py:248). */
+int os3d_add_table_rows(const void *x, const void *table, const int32_t *idx, int64_t m, int c, int elem_size, void *out,
+                        void *stream);
 
 /* In-place L2 normalisation of every head slice of q and k rows (F.normalize, eps 1e-12).
  * replaces: cosine_msa.py:152-153. */

@@ -113,6 +113,41 @@ static int launch_ln(const T *x, const T *resid, const float *w, const float *b,
 
 using namespace os3d;
 
+// out[r, :] = x[r, :] + table[idx[r], :]   (q = k = x + pos: the position embedding takes only window-volume many values,
+// so it is a small L2-resident table indexed by the in-window position instead of an [M, C] tensor in HBM)
+template <typename T>
+__global__ void __launch_bounds__(256) add_table_rows_kernel(const T *__restrict__ x, const T *__restrict__ table,
+                                                              const int32_t *__restrict__ idx, int64_t m, int chunks,
+                                                              T *__restrict__ out) {
+  const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= m * chunks) return;
+  const int64_t r = t / chunks;
+  const int c = (int)(t - r * chunks) * 8;
+  const int64_t c_total = (int64_t)chunks * 8;
+  float a[8], b[8];
+  Vec8<T>::load(x + r * c_total + c, a);
+  Vec8<T>::load(table + (int64_t)__ldg(idx + r) * c_total + c, b);
+#pragma unroll
+  for (int i = 0; i < 8; ++i) a[i] += b[i];
+  Vec8<T>::store(out + r * c_total + c, a);
+}
+
+extern "C" int os3d_add_table_rows(const void *x, const void *table, const int32_t *idx, int64_t m, int c, int elem_size,
+                                   void *out, void *stream) {
+  if (c <= 0 || c % 8 || (elem_size != 2 && elem_size != 4)) return OS3D_ERR_BAD_ARG;
+  if (m == 0) return 0;
+  const int chunks = c / 8;
+  const unsigned g = (unsigned)cdiv(m * chunks, 256);
+  if (elem_size == 2)
+    add_table_rows_kernel<__nv_bfloat16><<<g, 256, 0, (cudaStream_t)stream>>>(
+        (const __nv_bfloat16 *)x, (const __nv_bfloat16 *)table, idx, m, chunks, (__nv_bfloat16 *)out);
+  else
+    add_table_rows_kernel<float><<<g, 256, 0, (cudaStream_t)stream>>>((const float *)x, (const float *)table, idx, m,
+                                                                       chunks, (float *)out);
+  OS3D_LAUNCH_CHECK();
+  return 0;
+}
+
 extern "C" int os3d_layernorm_residual(const void *x, const void *resid, const float *w, const float *b, int64_t m, int c,
                                        float eps, int elem_size, void *out, void *stream) {
   if (c <= 0 || c % 8) return OS3D_ERR_BAD_ARG;

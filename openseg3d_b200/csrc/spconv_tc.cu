@@ -56,6 +56,13 @@ struct Params {
   const __nv_bfloat16 *residual;
   int flags;
   __nv_bfloat16 *out;
+  int64_t ldo;                // output row pitch in elements (>= cout)
+  int dense;                  // 1: the "kernel map" is the identity with one offset -- a plain Linear layer  (os3d_linear_bf16)
+  const float *ln_gamma, *ln_beta;   // flags & 8: LayerNorm over the cout columns of y before the residual add
+  float ln_eps;
+  const __nv_bfloat16 *table; // flags & 16: y[r, c] += table[tab_idx[r], c] for c < tab_cols (position-embedding term)
+  const int32_t *tab_idx;
+  int tab_cols;
   int tmem_cols, n_parts, n_per_part;
   uint32_t idesc;
   int tiles_per_cta, sa, sb;
@@ -77,6 +84,9 @@ __global__ void __launch_bounds__(kThreads, 2) spconv_tc_kernel(const Params p) 
   const uint32_t b_full = smem_u32(bars + 2 * kMaxSA), b_empty = smem_u32(bars + 2 * kMaxSA + kMaxSB);
   const uint32_t accum_bar = smem_u32(bars + 2 * kMaxSA + 2 * kMaxSB);
   uint32_t *masks_s = misc + 1;
+  // epilogue parameters staged in shared memory: with the carve-out at its maximum there is no L1 left, so a __ldg per
+  // 16-column chunk is a ~300-cycle trip to L2 in every epilogue iteration (ncu: 17 % of all stall samples)
+  float *prm_s = reinterpret_cast<float *>(misc + 18);    // [scale | shift | gamma | beta], cout floats each (16-byte aligned)
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int tile0 = blockIdx.x * p.tiles_per_cta;
@@ -88,7 +98,15 @@ __global__ void __launch_bounds__(kThreads, 2) spconv_tc_kernel(const Params p) 
     mbar_init(accum_bar, 1);
     fence_barrier_init();
   }
-  if (tid < kMaxTiles) masks_s[tid] = tid < ntile ? __ldg(p.tile_mask + tile0 + tid) : 0u;
+  if (tid < kMaxTiles) masks_s[tid] = tid < ntile ? (p.dense ? 1u : __ldg(p.tile_mask + tile0 + tid)) : 0u;
+  for (int i = tid; i < p.cout; i += kThreads) {
+    prm_s[i] = p.scale ? __ldg(p.scale + i) : 1.0f;
+    prm_s[p.cout + i] = p.shift ? __ldg(p.shift + i) : 0.0f;
+    if (p.flags & 8) {
+      prm_s[2 * p.cout + i] = __ldg(p.ln_gamma + i);
+      prm_s[3 * p.cout + i] = __ldg(p.ln_beta + i);
+    }
+  }
   __syncthreads();
   if (warp == kEpiWarps) tmem_alloc(smem_u32(&misc[0]), (uint32_t)p.tmem_cols);
   tc_fence_before();
@@ -141,13 +159,19 @@ __global__ void __launch_bounds__(kThreads, 2) spconv_tc_kernel(const Params p) 
           r = (slot - u0) & nprod_mask;
         }
       };
+      auto fetch_rows = [&]() -> int4 {
+        if (!p.dense) return __ldg(reinterpret_cast<const int4 *>(nt + (int64_t)ik * p.m_pad + it * kTileM));
+        const int64_t r = (int64_t)(tile0 + it) * kTileM + 4 * lane;      // Linear: row r of the output reads row r
+        return make_int4(r < p.m_out ? (int)r : -1, r + 1 < p.m_out ? (int)r + 1 : -1, r + 2 < p.m_out ? (int)r + 2 : -1,
+                         r + 3 < p.m_out ? (int)r + 3 : -1);
+      };
       // neighbour rows are prefetched TWO slots ahead: one slot's work is shorter than a trip to L2 / HBM for the table
       int4 v0 = make_int4(-1, -1, -1, -1), v1 = v0;
       int cb0 = 0, cb1 = 0;
       bool have0 = next_mine();
-      if (have0) { cb0 = icb; v0 = __ldg(reinterpret_cast<const int4 *>(nt + (int64_t)ik * p.m_pad + it * kTileM)); }
+      if (have0) { cb0 = icb; v0 = fetch_rows(); }
       bool have1 = have0 && next_mine();
-      if (have1) { cb1 = icb; v1 = __ldg(reinterpret_cast<const int4 *>(nt + (int64_t)ik * p.m_pad + it * kTileM)); }
+      if (have1) { cb1 = icb; v1 = fetch_rows(); }
       uint32_t ph = 1;                                     // empty barriers start "free"
       while (have0) {
         const int4 cur = v0;
@@ -156,7 +180,7 @@ __global__ void __launch_bounds__(kThreads, 2) spconv_tc_kernel(const Params p) 
         const char *src0 = in_bytes + ch * 2u;
         have0 = have1; v0 = v1; cb0 = cb1;
         have1 = have1 && next_mine();
-        if (have1) { cb1 = icb; v1 = __ldg(reinterpret_cast<const int4 *>(nt + (int64_t)ik * p.m_pad + it * kTileM)); }
+        if (have1) { cb1 = icb; v1 = fetch_rows(); }
         mbar_wait(empty_bar, ph);
         ph ^= 1;
 #pragma unroll
@@ -257,69 +281,154 @@ __global__ void __launch_bounds__(kThreads, 2) spconv_tc_kernel(const Params p) 
     tc_fence_after();
     const int quarter = warp & 3;                       // TMEM lanes [32 q, 32 q + 32) are visible to warps q and q + 4
     const bool pair_sum = (p.flags & 2) != 0;           // residual rows hold 2*cout channels; add r[2c] + r[2c+1] after the ReLU
-    const bool do_relu = (p.flags & 1) != 0;
-    for (int t = 0; t < ntile; ++t) {
-      const bool has = masks_s[t] != 0u;
-      const int64_t row = (int64_t)(tile0 + t) * kTileM + quarter * 32 + lane;
-      const bool row_ok = row < p.m_out;
-      __nv_bfloat16 *orow = p.out + row * p.cout;
-      const __nv_bfloat16 *rrow = p.residual ? p.residual + row * p.cout * (pair_sum ? 2 : 1) : nullptr;
-      for (int col = (warp >> 2) * 16; col < p.cout; col += 16 * (kEpiWarps / 4)) {
-        uint32_t v[16];
-        if (has) {
-          tmem_ld16(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(t * p.cout + col), v);
-          tmem_ld_wait();
-        } else {
+    const bool do_relu = (p.flags & 1) != 0, do_gelu = (p.flags & 4) != 0, do_ln = (p.flags & 8) != 0;
+    const bool do_tab = (p.flags & 16) != 0;
+    // y[0..16) = acc * scale + shift for columns [col, col + 16) of this thread's row of tile t
+    auto load16 = [&](int t, int col, bool has, float (&y)[16]) {
+      uint32_t v[16];
+      if (has) {
+        tmem_ld16(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(t * p.cout + col), v);
+        tmem_ld_wait();
+      } else {
 #pragma unroll
-          for (int i = 0; i < 16; ++i) v[i] = 0u;
+        for (int i = 0; i < 16; ++i) v[i] = 0u;
+      }
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const float4 sc = *reinterpret_cast<const float4 *>(prm_s + col + 4 * q);
+        const float4 sh = *reinterpret_cast<const float4 *>(prm_s + p.cout + col + 4 * q);
+        y[4 * q + 0] = fmaf(__uint_as_float(v[4 * q + 0]), sc.x, sh.x);
+        y[4 * q + 1] = fmaf(__uint_as_float(v[4 * q + 1]), sc.y, sh.y);
+        y[4 * q + 2] = fmaf(__uint_as_float(v[4 * q + 2]), sc.z, sh.z);
+        y[4 * q + 3] = fmaf(__uint_as_float(v[4 * q + 3]), sc.w, sh.w);
+      }
+    };
+    auto add_bf16x16 = [&](const uint4 &ra, const uint4 &rb, float (&y)[16]) {
+      const uint32_t rw[8] = {ra.x, ra.y, ra.z, ra.w, rb.x, rb.y, rb.z, rb.w};
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        y[2 * i] += __uint_as_float(rw[i] << 16);
+        y[2 * i + 1] += __uint_as_float(rw[i] & 0xffff0000u);
+      }
+    };
+    auto store16 = [&](__nv_bfloat16 *dst, const float (&y)[16]) {
+      uint32_t o[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const __nv_bfloat162 h = __floats2bfloat162_rn(y[2 * i], y[2 * i + 1]);
+        o[i] = *reinterpret_cast<const uint32_t *>(&h);
+      }
+      reinterpret_cast<uint4 *>(dst)[0] = make_uint4(o[0], o[1], o[2], o[3]);
+      reinterpret_cast<uint4 *>(dst)[1] = make_uint4(o[4], o[5], o[6], o[7]);
+    };
+    const uint4 zero4 = make_uint4(0, 0, 0, 0);
+    const int half = warp >> 2;                          // the two warps of a lane quarter take alternate 16-column chunks
+    if (do_ln) {
+      // out = residual + LayerNorm(y) * gamma + beta.  A thread owns a row (lane = row) of alternate 16-column chunks;
+      // the two warps of a lane quarter exchange their partial (sum, sum of squares) through shared memory (the A
+      // ring is free by now) at a 64-thread named barrier.  Two passes over the accumulator in TMEM; the residual
+      // rows (global, uncoalesced, L2 latency) are fetched one chunk ahead.
+      // (EncoderLayer: x + LN(attn(x)), x + LN(mlp(x)), point_transformer_layer.py:288-298.)
+      float2 *part = reinterpret_cast<float2 *>(smem);                 // [8 warps][32 lanes]
+      for (int t = 0; t < ntile; ++t) {
+        const bool has = masks_s[t] != 0u;
+        const int64_t row = (int64_t)(tile0 + t) * kTileM + quarter * 32 + lane;
+        const bool row_ok = row < p.m_out;
+        const __nv_bfloat16 *rrow = (p.residual && row_ok) ? p.residual + row * p.cout : nullptr;
+        uint4 na = zero4, nb = zero4;
+        if (rrow && half * 16 < p.cout) {
+          na = __ldg(reinterpret_cast<const uint4 *>(rrow + half * 16));
+          nb = __ldg(reinterpret_cast<const uint4 *>(rrow + half * 16) + 1);
         }
-        if (row_ok) {
+        float sum = 0.0f, sq = 0.0f;
+        for (int col = half * 16; col < p.cout; col += 32) {
           float y[16];
+          load16(t, col, has, y);
 #pragma unroll
-          for (int i = 0; i < 16; ++i) y[i] = __uint_as_float(v[i]);
-          if (p.scale) {
+          for (int i = 0; i < 16; ++i) { sum += y[i]; sq = fmaf(y[i], y[i], sq); }
+        }
+        part[warp * 32 + lane] = make_float2(sum, sq);
+        asm volatile("bar.sync %0, 64;" ::"r"(1 + quarter) : "memory");
+        const float2 other = part[(warp ^ 4) * 32 + lane];
+        asm volatile("bar.sync %0, 64;" ::"r"(1 + quarter) : "memory");      // partner has read before the next tile overwrites
+        sum += other.x;
+        sq += other.y;
+        const float mean = sum / (float)p.cout;
+        const float rstd = rsqrtf(fmaxf(sq / (float)p.cout - mean * mean, 0.0f) + p.ln_eps);
+        for (int col = half * 16; col < p.cout; col += 32) {
+          const uint4 ra = na, rb = nb;
+          if (rrow && col + 32 < p.cout) {
+            na = __ldg(reinterpret_cast<const uint4 *>(rrow + col + 32));
+            nb = __ldg(reinterpret_cast<const uint4 *>(rrow + col + 32) + 1);
+          }
+          float y[16];
+          load16(t, col, has, y);
+          if (row_ok) {
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
-              const float4 sc = __ldg(reinterpret_cast<const float4 *>(p.scale + col) + q);
-              const float4 sh = __ldg(reinterpret_cast<const float4 *>(p.shift + col) + q);
-              y[4 * q + 0] = fmaf(y[4 * q + 0], sc.x, sh.x);
-              y[4 * q + 1] = fmaf(y[4 * q + 1], sc.y, sh.y);
-              y[4 * q + 2] = fmaf(y[4 * q + 2], sc.z, sh.z);
-              y[4 * q + 3] = fmaf(y[4 * q + 3], sc.w, sh.w);
+              const float4 g = *reinterpret_cast<const float4 *>(prm_s + 2 * p.cout + col + 4 * q);
+              const float4 be = *reinterpret_cast<const float4 *>(prm_s + 3 * p.cout + col + 4 * q);
+              y[4 * q + 0] = fmaf((y[4 * q + 0] - mean) * rstd, g.x, be.x);
+              y[4 * q + 1] = fmaf((y[4 * q + 1] - mean) * rstd, g.y, be.y);
+              y[4 * q + 2] = fmaf((y[4 * q + 2] - mean) * rstd, g.z, be.z);
+              y[4 * q + 3] = fmaf((y[4 * q + 3] - mean) * rstd, g.w, be.w);
             }
+            if (rrow) add_bf16x16(ra, rb, y);
+            store16(p.out + row * p.ldo + col, y);
+          }
+        }
+      }
+    } else {
+      for (int t = 0; t < ntile; ++t) {
+        const bool has = masks_s[t] != 0u;
+        const int64_t row = (int64_t)(tile0 + t) * kTileM + quarter * 32 + lane;
+        const bool row_ok = row < p.m_out;
+        __nv_bfloat16 *orow = p.out + row * p.ldo;
+        const __nv_bfloat16 *rrow = (p.residual && row_ok) ? p.residual + row * p.cout * (pair_sum ? 2 : 1) : nullptr;
+        const __nv_bfloat16 *trow = (do_tab && row_ok) ? p.table + (int64_t)__ldg(p.tab_idx + row) * p.tab_cols : nullptr;
+        // additive row terms (table row before the activation, plain residual) are fetched one chunk ahead
+        uint4 nx[4] = {zero4, zero4, zero4, zero4};
+        auto fetch = [&](int col) {
+          if (trow && col < p.tab_cols) {
+            nx[0] = __ldg(reinterpret_cast<const uint4 *>(trow + col));
+            nx[1] = __ldg(reinterpret_cast<const uint4 *>(trow + col) + 1);
+          } else {
+            nx[0] = nx[1] = zero4;
           }
           if (rrow && !pair_sum) {
-            const uint4 ra = __ldg(reinterpret_cast<const uint4 *>(rrow + col));
-            const uint4 rb = __ldg(reinterpret_cast<const uint4 *>(rrow + col) + 1);
-            const uint32_t rw[8] = {ra.x, ra.y, ra.z, ra.w, rb.x, rb.y, rb.z, rb.w};
+            nx[2] = __ldg(reinterpret_cast<const uint4 *>(rrow + col));
+            nx[3] = __ldg(reinterpret_cast<const uint4 *>(rrow + col) + 1);
+          }
+        };
+        if (half * 16 < p.cout) fetch(half * 16);
+        for (int col = half * 16; col < p.cout; col += 32) {
+          const uint4 c0 = nx[0], c1 = nx[1], c2 = nx[2], c3 = nx[3];
+          if (col + 32 < p.cout) fetch(col + 32);
+          float y[16];
+          load16(t, col, has, y);
+          if (row_ok) {
+            add_bf16x16(c0, c1, y);
+            if (rrow && !pair_sum) add_bf16x16(c2, c3, y);
+            if (do_relu) {
 #pragma unroll
-            for (int i = 0; i < 8; ++i) {
-              y[2 * i] += __uint_as_float(rw[i] << 16);
-              y[2 * i + 1] += __uint_as_float(rw[i] & 0xffff0000u);
+              for (int i = 0; i < 16; ++i) y[i] = fmaxf(y[i], 0.0f);
             }
-          }
-          if (do_relu) {
+            if (do_gelu) {               // exact (erf) GELU, nn.GELU() default (point_transformer_layer.py:266)
 #pragma unroll
-            for (int i = 0; i < 16; ++i) y[i] = fmaxf(y[i], 0.0f);
-          }
-          if (rrow && pair_sum) {      // UpBlock: x_m + channel_reduction(cat)  (pointtransformer.py:89-110)
-#pragma unroll
-            for (int q = 0; q < 4; ++q) {
-              const uint4 r4 = __ldg(reinterpret_cast<const uint4 *>(rrow + 2 * col) + q);
-              const uint32_t rw[4] = {r4.x, r4.y, r4.z, r4.w};
-#pragma unroll
-              for (int i = 0; i < 4; ++i)
-                y[4 * q + i] += __uint_as_float(rw[i] << 16) + __uint_as_float(rw[i] & 0xffff0000u);
+              for (int i = 0; i < 16; ++i) y[i] = 0.5f * y[i] * (1.0f + erff(y[i] * 0.70710678118654752f));
             }
-          }
-          uint32_t o[8];
+            if (rrow && pair_sum) {      // UpBlock: x_m + channel_reduction(cat)  (pointtransformer.py:89-110)
 #pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            const __nv_bfloat162 h = __floats2bfloat162_rn(y[2 * i], y[2 * i + 1]);
-            o[i] = *reinterpret_cast<const uint32_t *>(&h);
+              for (int q = 0; q < 4; ++q) {
+                const uint4 r4 = __ldg(reinterpret_cast<const uint4 *>(rrow + 2 * col) + q);
+                const uint32_t rw[4] = {r4.x, r4.y, r4.z, r4.w};
+#pragma unroll
+                for (int i = 0; i < 4; ++i)
+                  y[4 * q + i] += __uint_as_float(rw[i] << 16) + __uint_as_float(rw[i] & 0xffff0000u);
+              }
+            }
+            store16(orow + col, y);
           }
-          reinterpret_cast<uint4 *>(orow + col)[0] = make_uint4(o[0], o[1], o[2], o[3]);
-          reinterpret_cast<uint4 *>(orow + col)[1] = make_uint4(o[4], o[5], o[6], o[7]);
         }
       }
     }
@@ -361,10 +470,10 @@ __global__ void __launch_bounds__(256) kernel_map_tiles_kernel(const int32_t *__
 // spconv 2.x weight [cout, 27, cin] f32 -> bf16 UMMA image [27 * ncb][cout][8 chunks, XOR-swizzled by row & 7][8]:
 // exactly the bytes a weight K-block occupies in shared memory, so one bulk copy loads it.  K-blocks never straddle
 // kernel offsets (the last channel block of an offset is zero-padded to 64).
-__global__ void pack_weight_img_kernel(const float *__restrict__ src, int cin, int cout, int ncb,
+__global__ void pack_weight_img_kernel(const float *__restrict__ src, int cin, int cout, int ncb, int kvol,
                                        __nv_bfloat16 *__restrict__ dst) {
   const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  const int64_t total = (int64_t)OS3D_KVOL * ncb * cout * kBlockK;
+  const int64_t total = (int64_t)kvol * ncb * cout * kBlockK;
   if (t >= total) return;
   const int e = (int)(t & 7);
   const int pc = (int)((t >> 3) & 7);
@@ -372,7 +481,7 @@ __global__ void pack_weight_img_kernel(const float *__restrict__ src, int cin, i
   const int blk = (int)((t >> 6) / cout);
   const int c = pc ^ (n & 7);  // logical chunk stored at physical chunk pc
   const int k = blk / ncb, ch = (blk - k * ncb) * kBlockK + c * 8 + e;
-  dst[t] = __float2bfloat16(ch < cin ? src[((int64_t)n * OS3D_KVOL + k) * cin + ch] : 0.0f);
+  dst[t] = __float2bfloat16(ch < cin ? src[((int64_t)n * kvol + k) * cin + ch] : 0.0f);
 }
 
 }  // namespace tc
@@ -401,7 +510,52 @@ extern "C" int os3d_pack_weight_bf16(const float *w_spconv, int cin, int cout, v
   const int ncb = (int)cdiv(cin, tc::kBlockK);
   const int64_t total = (int64_t)OS3D_KVOL * ncb * cout * tc::kBlockK;
   tc::pack_weight_img_kernel<<<(unsigned)cdiv(total, 256), 256, 0, (cudaStream_t)stream>>>(
-      w_spconv, cin, cout, ncb, (__nv_bfloat16 *)w_packed);
+      w_spconv, cin, cout, ncb, OS3D_KVOL, (__nv_bfloat16 *)w_packed);
+  OS3D_LAUNCH_CHECK();
+  return 0;
+}
+
+// Shared launch: geometry of the accumulators / rings for one (m_out, cin, cout) problem.
+static int launch_tc(tc::Params &p, cudaStream_t stream) {
+  const int cout = p.cout;
+  p.n_parts = cout > 256 ? 2 : 1;
+  p.n_per_part = cout / p.n_parts;
+  p.idesc = ptx::make_idesc_bf16(tc::kTileM, p.n_per_part);
+  // Occupancy first: what paces this kernel for small Cout is the serial work of ONE MMA-issuing warp per CTA
+  // (barrier round trips, proxy fence, issue), so two or three co-resident CTAs beat one CTA with a deep ring
+  // (measured sweep: gpurun_out/sweep_cfg.log, DESIGN.md).  Per CTA: T accumulators (T * Cout <= 512 / ctas TMEM
+  // columns), a weight ring of sb slabs and an A ring of sa (power of two) 16 KB slots within 227 KB / ctas.
+  const int ctas = cout <= 256 ? 2 : 1;
+  int tiles = (512 / ctas) / cout;
+  tiles = tiles > 5 ? 5 : tiles < 1 ? 1 : tiles;
+  while (tiles > 1 && cdiv(p.n_tiles, tiles) < 2 * 148 * ctas) --tiles;
+  { const char *e = getenv("OS3D_SPCONV_TILES");   // tuning / test override of the accumulators per CTA
+    if (e && atoi(e) > 0) tiles = min(atoi(e), min(512 / cout, tc::kMaxTiles)); }
+  p.tiles_per_cta = tiles;
+  int cols = 32;
+  while (cols < tiles * cout) cols <<= 1;
+  p.tmem_cols = cols;
+  const int b_bytes = cout * 128;
+  const int tail = (2 * tc::kMaxSA + 2 * tc::kMaxSB + 1) * 8 + 16 * 4 + 4 * cout * 4 + 64;   // barriers, misc, epilogue parameters
+  const int budget = (227 * 1024) / ctas - 1024 - tail - (ctas > 1 ? 1024 : 0);   // 1 KB per CTA is reserved by the driver
+  int sb = 3;
+  while (sb > 2 && budget - sb * b_bytes < 2 * tc::kATileBytes) --sb;
+  int sa = (budget - sb * b_bytes) / tc::kATileBytes;
+  { const char *e = getenv("OS3D_SPCONV_SA"); if (e && atoi(e) > 0 && atoi(e) < sa) sa = atoi(e); }
+  int sa_log2 = 3;                                           // ring depth: a power of two (index / phase from one counter)
+  while (sa_log2 > 0 && (1 << sa_log2) > sa) --sa_log2;
+  sa = 1 << sa_log2;
+  if (sa < 2 || (budget - sb * b_bytes) < sa * tc::kATileBytes) return OS3D_ERR_BAD_ARG;
+  p.sa = sa;
+  p.sa_log2 = sa_log2;
+  p.sb = sb;
+  const int smem = 1024 + sa * tc::kATileBytes + sb * b_bytes + tail;
+  static bool configured = false;
+  if (!configured) {
+    OS3D_CUDA(cudaFuncSetAttribute(tc::spconv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    configured = true;
+  }
+  tc::spconv_tc_kernel<<<(unsigned)cdiv(p.n_tiles, tiles), tc::kThreads, smem, stream>>>(p);
   OS3D_LAUNCH_CHECK();
   return 0;
 }
@@ -430,44 +584,66 @@ extern "C" int os3d_spconv_fwd_bf16(const void *in, int64_t m_in, const int32_t 
   p.residual = (const __nv_bfloat16 *)residual;
   p.flags = flags;
   p.out = (__nv_bfloat16 *)out;
-  p.n_parts = cout > 256 ? 2 : 1;
-  p.n_per_part = cout / p.n_parts;
-  p.idesc = ptx::make_idesc_bf16(tc::kTileM, p.n_per_part);
-  // Occupancy first: what paces this kernel for small Cout is the serial work of ONE MMA-issuing warp per CTA
-  // (barrier round trips, proxy fence, issue), so two or three co-resident CTAs beat one CTA with a deep ring
-  // (measured sweep: gpurun_out/sweep_cfg.log, DESIGN.md).  Per CTA: T accumulators (T * Cout <= 512 / ctas TMEM
-  // columns), a weight ring of sb slabs and an A ring of sa (power of two) 16 KB slots within 227 KB / ctas.
-  const int ctas = cout <= 256 ? 2 : 1;
-  int tiles = (512 / ctas) / cout;
-  tiles = tiles > 5 ? 5 : tiles < 1 ? 1 : tiles;
-  while (tiles > 1 && cdiv(p.n_tiles, tiles) < 2 * 148 * ctas) --tiles;
-  { const char *e = getenv("OS3D_SPCONV_TILES");   // tuning / test override of the accumulators per CTA
-    if (e && atoi(e) > 0) tiles = min(atoi(e), min(512 / cout, tc::kMaxTiles)); }
-  p.tiles_per_cta = tiles;
-  int cols = 32;
-  while (cols < tiles * cout) cols <<= 1;
-  p.tmem_cols = cols;
-  const int b_bytes = cout * 128;
-  const int tail = (2 * tc::kMaxSA + 2 * tc::kMaxSB + 1) * 8 + (1 + tc::kMaxTiles) * 4 + 64;
-  const int budget = (227 * 1024) / ctas - 1024 - tail - (ctas > 1 ? 1024 : 0);   // 1 KB per CTA is reserved by the driver
-  int sb = 3;
-  while (sb > 2 && budget - sb * b_bytes < 2 * tc::kATileBytes) --sb;
-  int sa = (budget - sb * b_bytes) / tc::kATileBytes;
-  { const char *e = getenv("OS3D_SPCONV_SA"); if (e && atoi(e) > 0 && atoi(e) < sa) sa = atoi(e); }
-  int sa_log2 = 3;                                           // ring depth: a power of two (index / phase from one counter)
-  while (sa_log2 > 0 && (1 << sa_log2) > sa) --sa_log2;
-  sa = 1 << sa_log2;
-  if (sa < 2 || (budget - sb * b_bytes) < sa * tc::kATileBytes) return OS3D_ERR_BAD_ARG;
-  p.sa = sa;
-  p.sa_log2 = sa_log2;
-  p.sb = sb;
-  const int smem = 1024 + sa * tc::kATileBytes + sb * b_bytes + tail;
-  static bool configured = false;
-  if (!configured) {
-    OS3D_CUDA(cudaFuncSetAttribute(tc::spconv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    configured = true;
-  }
-  tc::spconv_tc_kernel<<<(unsigned)cdiv(p.n_tiles, tiles), tc::kThreads, smem, (cudaStream_t)stream>>>(p);
+  p.ldo = cout;
+  p.dense = 0;
+  p.ln_gamma = p.ln_beta = nullptr;
+  p.ln_eps = 0.0f;
+  p.table = nullptr;
+  p.tab_idx = nullptr;
+  p.tab_cols = 0;
+  return launch_tc(p, (cudaStream_t)stream);
+}
+
+extern "C" int os3d_linear_bf16_packed_elems(int k, int n, int64_t *elems) {
+  if (k <= 0 || k % 8 || n <= 0) return OS3D_ERR_BAD_ARG;
+  *elems = cdiv(k, tc::kBlockK) * n * tc::kBlockK;
+  return 0;
+}
+
+extern "C" int os3d_pack_linear_bf16(const float *w, int k, int n, void *w_packed, void *stream) {
+  if (k <= 0 || n <= 0) return OS3D_ERR_BAD_ARG;
+  const int ncb = (int)cdiv(k, tc::kBlockK);
+  const int64_t total = (int64_t)ncb * n * tc::kBlockK;
+  tc::pack_weight_img_kernel<<<(unsigned)cdiv(total, 256), 256, 0, (cudaStream_t)stream>>>(w, k, n, ncb, 1,
+                                                                                         (__nv_bfloat16 *)w_packed);
   OS3D_LAUNCH_CHECK();
   return 0;
+}
+
+extern "C" int os3d_linear_bf16(const void *x, int64_t m, int k, int n, const void *w, const float *bias, int flags,
+                                const void *residual, const float *ln_gamma, const float *ln_beta, float ln_eps,
+                                const void *table, const int32_t *tab_idx, int tab_cols, void *out, int64_t ldo,
+                                void *stream) {
+  if (k <= 0 || k % 8 || n < 16 || n % 16 || n > 512 || (n > 256 && n % 32) || m < 0 || ((uintptr_t)x & 15) ||
+      (flags & ~(1 | 4 | 8 | 16)) || ((flags & 8) && (!ln_gamma || !ln_beta || (flags & 16))) ||
+      ((flags & 16) && (!table || !tab_idx || tab_cols % 16 || tab_cols > n)) || ldo < n || ldo % 8 ||
+      ((uintptr_t)out & 15))
+    return OS3D_ERR_BAD_ARG;
+  if (m == 0) return 0;
+  tc::Params p;
+  p.in = (const __nv_bfloat16 *)x;
+  p.cin = k;
+  p.nbr_t = nullptr;
+  p.tile_mask = nullptr;
+  p.m_out = m;
+  p.n_tiles = (int)cdiv(m, tc::kTileM);
+  p.m_pad = (int64_t)p.n_tiles * tc::kTileM;
+  p.cin16 = (k + 15) / 16 * 16;
+  p.cout = n;
+  p.ncb = (int)cdiv(k, tc::kBlockK);
+  p.w_img = (const __nv_bfloat16 *)w;
+  p.scale = nullptr;
+  p.shift = bias;
+  p.residual = (const __nv_bfloat16 *)residual;
+  p.flags = flags;
+  p.out = (__nv_bfloat16 *)out;
+  p.ldo = ldo;
+  p.dense = 1;
+  p.ln_gamma = ln_gamma;
+  p.ln_beta = ln_beta;
+  p.ln_eps = ln_eps;
+  p.table = (const __nv_bfloat16 *)table;
+  p.tab_idx = tab_idx;
+  p.tab_cols = tab_cols;
+  return launch_tc(p, (cudaStream_t)stream);
 }

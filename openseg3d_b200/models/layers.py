@@ -18,6 +18,7 @@ import torch.nn.functional as F
 from .. import _lib
 from .._lib import WindowCfg
 from ..ops.pooling import scatter_mean
+from ..ops.linear import PackedLinearCache, linear_bf16
 
 
 class WindowSegments(object):
@@ -83,6 +84,53 @@ def window2flat(feat_3d_dict, inds):
     return out
 
 
+class PosDict(dict):
+    """``pos_dict_shift{i}``.  'flat' ([M, C] sinusoidal embedding, point_transformer_layer.py:152-207) is computed on
+    first access: the bf16 hot path never needs it, because (x + pos) W^T = x W^T + pos W^T and pos takes only
+    window-volume many values -- it uses ``table`` ([win_z * win_y * win_x, C] fp32) and ``pos_idx`` (int32 [M], the
+    table row of each voxel) instead."""
+
+    def __init__(self, layer, seg, feat_dim, dtype):
+        super().__init__()
+        self._layer, self._seg, self._c, self._dtype = layer, seg, feat_dim, dtype
+        self._idx = None
+
+    def __missing__(self, key):
+        if key != 'flat':
+            raise KeyError(key)
+        self['flat'] = self._layer.get_pos_embed(self._seg, self._c, self._dtype)
+        return self['flat']
+
+    @property
+    def table(self):
+        return self._layer.pos_table(self._c, self._seg.in_win.device)
+
+    def table_as(self, dtype):
+        hit = self.__dict__.get('_tab_cast')
+        if hit is None or hit.dtype != dtype:
+            hit = self.table.to(dtype).contiguous()
+            self.__dict__['_tab_cast'] = hit
+        return hit
+
+    def add_to(self, x):
+        """x + pos without materialising pos: one gather-add from the table (os3d_add_table_rows)."""
+        x = x.contiguous()
+        if x.shape[1] % 8:
+            return x + self['flat'].to(x.dtype)
+        out = torch.empty_like(x)
+        _lib.call('os3d_add_table_rows', x, self.table_as(x.dtype), self.pos_idx, x.shape[0], x.shape[1], x.element_size(),
+                  out)
+        return out
+
+    @property
+    def pos_idx(self):
+        if self._idx is None:
+            wx, wy, wz = [int(w) for w in self._layer.window_shape]
+            iw = self._seg.in_win                      # (z, y, x)
+            self._idx = ((iw[:, 0] * wy + iw[:, 1]) * wx + iw[:, 2]).contiguous()
+        return self._idx
+
+
 class SparseWindowPartitionLayer(nn.Module):
     """Same constructor and output keys as point_transformer_layer.py:11-69.  forward(x) -> dict with
     batch_win_inds_shift{0,1}, coors_in_win_shift{0,1}, voxel_features, voxel_coords, voxel_keep_inds,
@@ -99,6 +147,20 @@ class SparseWindowPartitionLayer(nn.Module):
         self.window_shape = window_shape
         self.normalize_pos = normalize_pos
         self.pos_temperature = pos_temperature
+        self._tables = {}
+
+    @torch.no_grad()
+    def pos_table(self, feat_dim, device):
+        """fp32 embedding of every in-window position, row (z * win_y + y) * win_x + x."""
+        key = (feat_dim, str(device))
+        if key not in self._tables:
+            wx, wy, wz = [int(w) for w in self.window_shape]
+            z, y, x = torch.meshgrid(torch.arange(wz), torch.arange(wy), torch.arange(wx), indexing='ij')
+            grid = torch.stack([z, y, x], dim=-1).reshape(-1, 3).int().to(device).contiguous()
+            out = torch.empty((grid.shape[0], feat_dim), dtype=torch.float32, device=device)
+            _lib.call('os3d_pos_embed', grid, grid.shape[0], feat_dim, wx, wy, wz, float(self.pos_temperature), 4, out)
+            self._tables[key] = out
+        return self._tables[key]
 
     def _cfg(self, do_shift):
         """get_window_coors' scalar setup, swformer_utils.py:109-131."""
@@ -168,7 +230,7 @@ class SparseWindowPartitionLayer(nn.Module):
             info[f'voxel_batching_level_shift{i}'] = seg.level
             info[f'flat2win_inds_shift{i}'] = Flat2WinInds(segments=seg, voxel_batching_level=seg.level,
                                                            batching_info=self.batching_info)
-            info[f'pos_dict_shift{i}'] = {'flat': self.get_pos_embed(seg, feats.shape[1], feats.dtype)}
+            info[f'pos_dict_shift{i}'] = PosDict(self, seg, feats.shape[1], feats.dtype)
             info[f'key_mask_shift{i}'] = {}     # padding masks are implicit in the segment lengths
         return info
 
@@ -224,24 +286,47 @@ class CosineMultiheadAttention(nn.MultiheadAttention):
             self._cast['pad'] = tuple(t.to(dtype).contiguous() for t in vals) + (dp,)
         return self._cast['pad']
 
-    def forward_segments(self, feat, pos, seg):
-        """feat, pos: flat [M, C]; seg: WindowSegments.  Returns [M, C]."""
+    def _out_proj_chunks(self):
+        """Head-padded output projection [C, H*dp] as a tensor-core image (PackedLinearCache chunks)."""
+        tag = (self.out_proj.weight._version, self.out_proj.weight.data_ptr())
+        hit = self.__dict__.get('_o_chunks')
+        if hit is None or hit[0] != tag:
+            _, _, _, _, w_o, b_o, _ = self.params_head_padded(torch.float32)
+            hit = (tag, PackedLinearCache().get('o', w_o, b_o, max_width=512))
+            self.__dict__['_o_chunks'] = hit
+        return hit[1]
+
+    def attention_heads(self, feat, pos_dict, seg):
+        """bf16 tensor-core path up to (not including) the output projection: returns ([M, H*dp] heads, out-proj chunks).
+        q, k are normalised inside the attention kernel's gather."""
+        m = feat.shape[0]
+        w_qk, b_qk, w_v, b_v, _, _, dp = self.params_head_padded(feat.dtype)
+        o_c = self._out_proj_chunks()
+        hd = self.num_heads * dp
+        # q / k / v projections are plain library GEMMs (cuBLAS); measured, os3d_linear_bf16 does not beat cuBLAS on
+        # them (DESIGN.md) -- it is used where a fused epilogue removes whole passes (out-proj / fc2 + LayerNorm).
+        qk = F.linear(pos_dict.add_to(feat) if pos_dict is not None else feat, w_qk, b_qk)   # [M, 2*H*dp]: q | k
+        v = F.linear(feat, w_v, b_v)                                                          # [M, H*dp]
+        out = torch.empty((m, hd), dtype=feat.dtype, device=feat.device)
+        _lib.call('os3d_window_attention_bf16_tc', qk, qk.data_ptr() + hd * 2, v, 2 * hd, hd, m, self.num_heads, dp,
+                  seg.order, seg.pos_seg, seg.level_info, self.tau.detach().float().reshape(1), float(self.tau_min),
+                  out, hd)
+        return out, o_c
+
+    def tensor_core_ok(self, feat):
+        return feat.dtype == torch.bfloat16 and self.embed_dim // self.num_heads <= 48 and self.embed_dim % 8 == 0
+
+    def forward_segments(self, feat, pos_dict, seg):
+        """feat: flat [M, C]; pos_dict: PosDict or None; seg: WindowSegments.  Returns [M, C]."""
         if self.training and self.dropout > 0:
             raise NotImplementedError('attention dropout (training) is not built yet')
         m, c = feat.shape
-        if feat.dtype == torch.bfloat16 and c // self.num_heads <= 48:
-            # tensor-core path: head-padded projections, normalisation folded into the attention kernel's gather
-            w_qk, b_qk, w_v, b_v, w_o, b_o, dp = self.params_head_padded(feat.dtype)
-            hd = self.num_heads * dp
-            qk = F.linear(feat + pos if pos is not None else feat, w_qk, b_qk)       # [M, 2*H*dp]
-            v = F.linear(feat, w_v, b_v)                                              # [M, H*dp]
-            out = torch.empty((m, hd), dtype=feat.dtype, device=feat.device)
-            _lib.call('os3d_window_attention_bf16_tc', qk, qk.data_ptr() + hd * 2, v, 2 * hd, hd, m, self.num_heads, dp,
-                      seg.order, seg.pos_seg, seg.level_info, self.tau.detach().float().reshape(1), float(self.tau_min),
-                      out, hd)
-            return F.linear(out, w_o, b_o)
+        if self.tensor_core_ok(feat):
+            heads, o_c = self.attention_heads(feat, pos_dict, seg)
+            return linear_bf16(heads, o_c)
         w_in, b_in, w_out, b_out = self.params(feat.dtype)
-        qk_in = feat + pos if pos is not None else feat
+        qk_in = (pos_dict.add_to(feat) if isinstance(pos_dict, PosDict) else feat + pos_dict['flat'].to(feat.dtype)) \
+            if pos_dict is not None else feat
         qk = F.linear(qk_in, w_in[:2 * c], b_in[:2 * c])           # [M, 2C]: q | k   (q = k = x + pos)
         v = F.linear(feat, w_in[2 * c:], b_in[2 * c:])             # [M, C]           (v = x)
         es = feat.element_size()
@@ -265,10 +350,7 @@ class WindowAttention(nn.Module):
         partition layer's pos_dict_shift{i} / flat2win_inds_shift{i}; key_padding_dict is unused (no padding exists)."""
         if feat_2d.dtype not in (torch.float32, torch.bfloat16):
             raise RuntimeError('window attention runs in float32 or bfloat16')
-        pos = pos_dict['flat'] if pos_dict is not None else None
-        if pos is not None and pos.dtype != feat_2d.dtype:
-            pos = pos.to(feat_2d.dtype)
-        return self.self_attn.forward_segments(feat_2d.contiguous(), pos, ind_dict['segments'])
+        return self.self_attn.forward_segments(feat_2d.contiguous(), pos_dict, ind_dict['segments'])
 
 
 def _cast_like(mod, name, dtype):
@@ -292,6 +374,10 @@ def linear_in(mod, x):
 def layer_norm_in(mod, x):
     return F.layer_norm(x, mod.normalized_shape, _cast_like(mod, 'weight', x.dtype), _cast_like(mod, 'bias', x.dtype),
                         mod.eps)
+
+
+def _ln_params(mod):
+    return (_cast_like(mod, 'weight', torch.float32), _cast_like(mod, 'bias', torch.float32), mod.eps)
 
 
 def residual_layer_norm(mod, x, resid):
@@ -350,6 +436,17 @@ class EncoderLayer(nn.Module):
         self.mlp = MLP(in_features=d_model, hidden_features=mlp_hidden_dim, drop=drop)
 
     def forward(self, x, pos_dict, ind_dict, key_padding_mask_dict=None):
+        mha = self.win_attn.self_attn
+        if not self.training and mha.tensor_core_ok(x) and isinstance(pos_dict, PosDict):
+            # bf16 inference: the two projections that are followed by residual + LayerNorm run on the tcgen05 kernel
+            # with that epilogue fused (os3d_linear_bf16): the [M, C] projection output never goes to HBM
+            x = x.contiguous()
+            heads, o_c = mha.attention_heads(x, pos_dict, ind_dict['segments'])
+            cache = self.__dict__.setdefault('_lin', PackedLinearCache())
+            x1 = linear_bf16(heads, o_c, residual=x, ln=_ln_params(self.norm1))
+            h = self.mlp.act(linear_in(self.mlp.fc1, x1))
+            return linear_bf16(h, cache.get('fc2', self.mlp.fc2.weight, self.mlp.fc2.bias, max_width=512), residual=x1,
+                               ln=_ln_params(self.norm2))
         attn = self.win_attn(x, pos_dict, ind_dict, key_padding_mask_dict)
         if self.training:
             x = x + self.drop_path(layer_norm_in(self.norm1, attn))

@@ -1,0 +1,87 @@
+"""nn.Linear on the tcgen05 kernel with the SWFormer epilogues fused (os3d_linear_bf16): bias, ReLU / exact GELU,
+residual + LayerNorm, and the position-embedding table term of the q / k projection.  bf16 activations only; there is
+no fallback -- other dtypes raise."""
+import ctypes
+
+import torch
+
+from .. import _lib
+
+RELU, GELU, LAYERNORM, TABLE = 1, 4, 8, 16
+
+
+class PackedLinearCache(object):
+    """Kernel-layout copies of Linear weights (the UMMA B-operand image) and fp32 biases, rebuilt when the source
+    parameter changes (version counter / storage)."""
+
+    def __init__(self):
+        self._store = {}
+
+    def get(self, key, weight, bias=None, max_width=256):
+        """``max_width``: widest output chunk per launch.  256 keeps two CTAs per SM (tensor memory: 512 columns);
+        the LayerNorm epilogue needs the whole row in one chunk (pass 512)."""
+        tag = (weight.data_ptr(), weight._version, weight.device,
+               None if bias is None else (bias.data_ptr(), bias._version))
+        hit = self._store.get(key)
+        if hit is not None and hit[0] == tag:
+            return hit[1]
+        n, k = weight.shape
+        if k % 8:
+            raise RuntimeError(f'linear_bf16: in_features {k} must be a multiple of 8')
+        w32 = weight.detach().float().contiguous()
+        chunks = []
+        n_chunks = (n + max_width - 1) // max_width
+        while n % n_chunks or (n // n_chunks) % 16:
+            n_chunks += 1
+        step = n // n_chunks
+        if n % n_chunks or step % (32 if step > 256 else 16):
+            raise RuntimeError(f'linear_bf16: out_features {n} cannot be cut into multiples of 16 (32 above 256)')
+        for c in range(n_chunks):
+            elems = ctypes.c_int64(0)
+            _lib.lib().os3d_linear_bf16_packed_elems(k, step, ctypes.byref(elems))
+            packed = torch.empty(elems.value, dtype=torch.bfloat16, device=weight.device)
+            _lib.call('os3d_pack_linear_bf16', w32[c * step:(c + 1) * step].contiguous(), k, step, packed)
+            b = None if bias is None else bias.detach().float()[c * step:(c + 1) * step].contiguous()
+            chunks.append((packed, b, c * step, step))
+        self._store[key] = (tag, chunks)
+        return chunks
+
+
+def linear_bf16(x, chunks, flags=0, residual=None, ln=None, table=None, tab_idx=None):
+    """out = epilogue(x @ W.T + b).  ``chunks``: PackedLinearCache.get(...).  ln = (gamma f32, beta f32, eps);
+    table: list of per-chunk [rows, width] bf16 tables (or one tensor when there is one chunk), tab_idx int32 [M]."""
+    _lib.require_cuda(x)
+    if x.dtype != torch.bfloat16:
+        raise RuntimeError('linear_bf16 takes bfloat16 activations')
+    x = x.contiguous()
+    m, k = x.shape
+    n = sum(c[3] for c in chunks)
+    out = torch.empty((m, n), dtype=torch.bfloat16, device=x.device)
+    if m == 0:
+        return out
+    if ln is not None:
+        flags |= LAYERNORM
+        if len(chunks) != 1:
+            raise RuntimeError('linear_bf16: the LayerNorm epilogue needs the whole row in one tile (out_features <= 512)')
+    if table is not None:
+        flags |= TABLE
+        if isinstance(table, torch.Tensor):
+            table = [table]
+    gamma, beta, eps = ln if ln is not None else (None, None, 0.0)
+    for i, (packed, bias, off, width) in enumerate(chunks):
+        tab = table[i] if table is not None else None
+        dst = out if off == 0 and width == n else out[:, off:]
+        _lib.lib()          # make sure the library is loaded before taking raw pointers
+        _lib.call('os3d_linear_bf16', x, m, k, width, packed, bias, flags,
+                  residual.contiguous() if residual is not None else None, gamma, beta, float(eps), tab, tab_idx,
+                  tab.shape[1] if tab is not None else 0, _Ptr(dst), n,
+                  work=lambda w=width: 2.0 * m * k * w)
+    return out
+
+
+class _Ptr(object):
+    """Raw device pointer argument (a column slice of a row-major tensor is not contiguous, its base pointer is all the
+    kernel needs: the row pitch is passed separately)."""
+
+    def __init__(self, t):
+        self.ptr = t.data_ptr()
