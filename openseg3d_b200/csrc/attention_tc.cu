@@ -71,9 +71,12 @@ __global__ void __launch_bounds__(kThreads, DP <= 32 ? 4 : 3) window_attention_t
   __shared__ uint32_t tmem_slot;
 
   const int tid = threadIdx.x, warp = tid >> 5;
-  const int h = blockIdx.y;
+  // heads of one query tile are adjacent in launch order: they run at the same time and share the q / k / v rows (each
+  // head reads a 32-96 byte slice of the same lines) while those are still in L2.  With heads on the slow grid axis
+  // every line came from HBM once per head (ncu: 3.1 GB of DRAM reads per launch for 0.7 GB of q / k / v).
+  const int h = blockIdx.x % p.heads;
   const int n_tok = __ldg(p.level_info + 14);
-  const int p0 = blockIdx.x * kTileQ;
+  const int p0 = (blockIdx.x / p.heads) * kTileQ;
   if (p0 >= n_tok) return;
   const int p_last = min(p0 + kTileQ, n_tok) - 1;
 
@@ -372,7 +375,7 @@ extern "C" int os3d_window_attention_bf16_tc(const void *q, const void *k, const
   p.tau_min = tau_min;
   p.out = (__nv_bfloat16 *)out;
   p.heads = heads;
-  dim3 grid((unsigned)cdiv(m, attn_tc::kTileQ), (unsigned)heads);
+  dim3 grid((unsigned)(cdiv(m, attn_tc::kTileQ) * heads));
   cudaStream_t st = (cudaStream_t)stream;
   if (dp == 16) attn_tc::window_attention_tc_kernel<16><<<grid, attn_tc::kThreads, 0, st>>>(p);
   else if (dp == 32) attn_tc::window_attention_tc_kernel<32><<<grid, attn_tc::kThreads, 0, st>>>(p);
