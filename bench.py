@@ -145,7 +145,8 @@ def main():
     dtype = torch.bfloat16 if args.dtype == 'bf16' else torch.float32
     model = build_segformer(CONFIG, compute_dtype=dtype).cuda().eval()
 
-    seeds = [rank * args.frames + i for i in range(args.frames)]
+    from openseg3d_b200.utils.sharding import frame_seeds, job_totals
+    seeds = frame_seeds(rank, args.frames)
     pts_np, _ = synthetic.make_batch(seeds, 1, False)
     n_points = pts_np.shape[0]
     host = torch.from_numpy(pts_np).pin_memory()
@@ -177,10 +178,7 @@ def main():
             fn()
         e1.record()
         barrier()
-        ms = torch.tensor([e0.elapsed_time(e1)], device='cuda')
-        if world > 1:
-            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
-        return float(ms.item())
+        return job_totals(0, e0.elapsed_time(e1), 'cuda')[1]          # MAX over ranks
 
     for _ in range(args.warmup):
         step_resident()
@@ -194,10 +192,7 @@ def main():
     step_e2e()
     e2e_ms = timed(step_e2e, args.steps)
 
-    tot_pts = torch.tensor([float(n_points)], device='cuda')
-    if world > 1:
-        dist.all_reduce(tot_pts)
-    total_points = float(tot_pts.item())
+    total_points = job_totals(n_points, 0.0, 'cuda')[0]               # SUM over ranks
     value = total_points * args.steps / (total_ms * 1e-3)
     e2e_value = total_points * args.steps / (e2e_ms * 1e-3)
 
