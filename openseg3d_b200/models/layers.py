@@ -487,5 +487,5 @@ class FlattenSELayer(nn.Module):
     def forward(self, x, indices, batch_size=None):
         indices = indices.long()
         pooled = scatter_mean(x, indices, batch_size)
-        gate = self.fc(pooled.to(x.dtype))
+        gate = self.fc(pooled.float()).to(x.dtype)          # B rows: fp32 whatever the activation dtype
         return x * gate[indices]

@@ -21,6 +21,70 @@ from .layers import FlattenSELayer
 from .voxel_encoders import VFE
 
 
+class FoldedMLP(object):
+    """Inference form of a point-wise MLP written as nn.Sequential([BN], (Linear, [BN], [ReLU], [Dropout])*)
+    (segformer.py:21-32,58-76): eval-mode BatchNorm1d is affine, so it folds into the neighbouring Linear
+    (y = s*(Wx + b) + t  ->  W' = s*W, b' = s*b + t; a leading BN folds into the first Linear's columns), and the ReLU
+    runs in the GEMM epilogue (cuBLASLt bias + ReLU).  The module tree / state_dict stay the reference's; this is
+    only how forward() executes them when not training.  Rebuilt when any parameter or buffer changes."""
+
+    def __init__(self, seq):
+        self.seq, self._tag, self._layers = seq, None, None
+
+    def _build(self):
+        mods = list(self.seq)
+        tag = tuple((t.data_ptr(), t._version) for m in mods for t in list(m.parameters()) + list(m.buffers()))
+        if tag == self._tag:
+            return self._layers
+
+        def affine(bn):
+            s = bn.weight.detach().float() * torch.rsqrt(bn.running_var.float() + bn.eps)
+            return s, bn.bias.detach().float() - bn.running_mean.float() * s
+
+        layers, pre, i = [], None, 0
+        if isinstance(mods[0], nn.BatchNorm1d):
+            pre, i = affine(mods[0]), 1
+        while i < len(mods):
+            lin = mods[i]
+            if not isinstance(lin, nn.Linear):
+                raise NotImplementedError(f'FoldedMLP: unexpected {type(lin).__name__} at position {i}')
+            w = lin.weight.detach().float()
+            b = lin.bias.detach().float() if lin.bias is not None else w.new_zeros(w.shape[0])
+            if pre is not None:                       # Linear(s*x + t) = (W*s) x + (W t + b)
+                b = b + w @ pre[1]
+                w = w * pre[0][None, :]
+                pre = None
+            i += 1
+            relu = False
+            while i < len(mods) and not isinstance(mods[i], nn.Linear):
+                m = mods[i]
+                if isinstance(m, nn.BatchNorm1d):
+                    if relu:
+                        raise NotImplementedError('FoldedMLP: BatchNorm after ReLU')
+                    sc, sh = affine(m)
+                    w, b = w * sc[:, None], b * sc + sh
+                elif isinstance(m, nn.ReLU):
+                    relu = True
+                elif not isinstance(m, nn.Dropout):
+                    raise NotImplementedError(f'FoldedMLP: unexpected {type(m).__name__}')
+                i += 1
+            layers.append((w.contiguous(), b.contiguous(), relu, {}))
+        self._tag, self._layers = tag, layers
+        return layers
+
+    def __call__(self, x, dtype):
+        """x: [N, C] fp32.  The first layer runs in fp32 (raw metric coordinates do not survive a bf16 cast), the rest
+        in ``dtype``."""
+        for li, (w, b, relu, cast) in enumerate(self._build()):
+            dt = torch.float32 if li == 0 and x.dtype == torch.float32 else dtype
+            if dt not in cast:
+                cast[dt] = (w.to(dt).t().contiguous(), b.to(dt))
+            wt, bb = cast[dt]
+            x = x.to(dt)
+            x = torch._addmm_activation(bb, x, wt) if relu else torch.addmm(bb, x, wt)
+        return x.to(dtype)
+
+
 class Segformer(nn.Module):
     def __init__(self, dataset, batching_info, window_shape, depths, drop_path_rate, compute_dtype=torch.float32):
         super().__init__()
@@ -64,6 +128,12 @@ class Segformer(nn.Module):
                                         nn.Linear(64, dataset.num_classes, bias=False))
         self.weight_initialization()
 
+    def _folded(self, name):
+        cache = self.__dict__.setdefault('_folded_mlps', {})
+        if name not in cache:
+            cache[name] = FoldedMLP(getattr(self, name))
+        return cache[name]
+
     def weight_initialization(self):
         for m in self.modules():
             if isinstance(m, (nn.Linear, nn.Conv2d)):
@@ -92,8 +162,12 @@ class Segformer(nn.Module):
             cur_points = points[cur_point_indices]
         else:
             cur_points = points
-        with torch.autocast('cuda', dtype=torch.bfloat16, enabled=bf16):
-            point_per_features = self.point_encoder(cur_points)
+        fold = not self.training                          # inference: BatchNorm folded, ReLU in the GEMM epilogue
+        if fold:
+            point_per_features = self._folded('point_encoder')(cur_points, self.compute_dtype)
+        else:
+            with torch.autocast('cuda', dtype=torch.bfloat16, enabled=bf16):
+                point_per_features = self.point_encoder(cur_points)
 
         # encode voxel features (fp32 pooling)
         if self.use_multi_sweeps:
@@ -106,12 +180,12 @@ class Segformer(nn.Module):
         # point features from the encoded voxel features
         ids = point_voxel_ids[cur_point_indices] if self.use_multi_sweeps else point_voxel_ids
         point_voxel_features = voxel_to_point(batch_dict['voxel_features'], ids)
-        with torch.autocast('cuda', dtype=torch.bfloat16, enabled=bf16):
+        with torch.autocast('cuda', dtype=torch.bfloat16, enabled=bf16 and not fold):
             fused = torch.cat([point_per_features.to(point_voxel_features.dtype), point_voxel_features], dim=1)
-            fused = self.fusion_encoder(fused)
+            fused = self._folded('fusion_encoder')(fused, self.compute_dtype) if fold else self.fusion_encoder(fused)
             batch_idx = raw[:, 0][cur_point_indices] if self.use_multi_sweeps else raw[:, 0]
             fused = fused + self.se(fused, batch_idx, batch_dict['batch_size'])
-            point_out = self.classifier(fused)
+            point_out = self._folded('classifier')(fused, self.compute_dtype) if fold else self.classifier(fused)
 
         result = OrderedDict()
         result['point_out'] = point_out

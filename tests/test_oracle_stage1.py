@@ -63,3 +63,28 @@ def test_scatter_semantics():
     counts = torch.tensor([1, 2])
     assert torch.allclose(oracle.voxel_avg_pooling(feats, torch.tensor([1, 5, 1, 0]), counts),
                           torch.tensor([[7., 8.], [-2., -4.]]))
+
+
+def test_folded_point_mlp_equals_sequential():
+    """Inference-time BatchNorm folding of the point-wise MLPs (segformer.py:21-32,58-76) is exact up to fp32
+    rounding: same nn.Sequential, same state_dict, evaluated both ways on CPU."""
+    import torch
+    import torch.nn as nn
+    from openseg3d_b200.models.segmentors import FoldedMLP
+    torch.manual_seed(0)
+    seq = nn.Sequential(nn.BatchNorm1d(6), nn.Linear(6, 64, bias=False), nn.BatchNorm1d(64), nn.ReLU(True),
+                        nn.Linear(64, 128, bias=False), nn.BatchNorm1d(128), nn.ReLU(True), nn.Dropout(0.3),
+                        nn.Linear(128, 22)).eval()
+    for m in seq:
+        if isinstance(m, nn.BatchNorm1d):
+            m.running_mean.normal_()
+            m.running_var.uniform_(0.5, 2)
+            m.weight.data.uniform_(0.5, 1.5)
+            m.bias.data.normal_()
+    x = torch.randn(1000, 6) * 30
+    folded = FoldedMLP(seq)
+    with torch.no_grad():
+        ref = seq(x)
+        assert (ref - folded(x, torch.float32)).abs().max() < 1e-4 * ref.abs().max()
+        seq[2].running_mean.add_(1.0)                 # buffers changed -> the folded copy is rebuilt
+        assert (seq(x) - folded(x, torch.float32)).abs().max() < 1e-4 * ref.abs().max()
