@@ -26,10 +26,8 @@ namespace attn_tc {
 using namespace ptx;
 
 constexpr int kTileQ = 128;
-constexpr int kBlockKeys = 64;
 constexpr int kThreads = 128;
 constexpr int kLbo = 128;                 // bytes between core matrices along K
-constexpr int kTmemCols = 128;            // S: [0, 64), O: [64, 64 + dp)
 
 struct Params {
   const __nv_bfloat16 *q, *k, *v;         // rows: q, k pitch ld (elements), v pitch ldv; head h at column h * dp
@@ -52,8 +50,13 @@ __device__ __forceinline__ float ex2_ftz(float x) {
 // smem offset of element chunk (row r, 16-byte K-chunk c) in the K-major no-swizzle layout with 8-row group stride sbo
 __device__ __forceinline__ uint32_t core_off(int r, int c, int sbo) { return (r >> 3) * sbo + c * kLbo + (r & 7) * 16; }
 
-template <int DP>
-__global__ void __launch_bounds__(kThreads, DP <= 32 ? 4 : 3) window_attention_tc_kernel(const Params p) {
+// DP: padded head dim.  KB: keys per block.  TMEM: S in columns [0, KB), O in [KB, KB + DP) of a power-of-two allocation
+// -- with KB = 32 and DP = 16 that is 64 columns, so 8 CTAs share an SM (and short windows waste half as many masked
+// score columns); KB = 64 otherwise (128 columns, 4 CTAs).
+template <int DP, int KB>
+__global__ void __launch_bounds__(kThreads, KB == 32 ? 8 : (DP <= 32 ? 4 : 3)) window_attention_tc_kernel(const Params p) {
+  constexpr int kBlockKeys = KB;
+  constexpr int kTmemCols = (KB + DP) <= 64 ? 64 : 128;
   constexpr int kChunks = DP / 8;                         // 16-byte chunks per head slice
   constexpr int kSboQ = kChunks * kLbo + 16;              // +16: stagger 8-row groups across banks
   constexpr int kSboP = (kBlockKeys / 8) * kLbo + 16;
@@ -155,13 +158,13 @@ __global__ void __launch_bounds__(kThreads, DP <= 32 ? 4 : 3) window_attention_t
   // Two threads per key; both read the whole K slice (the norm needs it), each stores the chunks c with (c & 1) == half
   // and transposes the same chunks of V.  The raw slices of block b+1 are fetched into registers while block b is in
   // its MMA / softmax phases, so the two dependent global loads (order -> row) are off the critical path.
-  const int key = tid >> 1, half = tid & 1;
+  const int key = tid >> 1, half = tid & 1;              // KB = 32: threads 64..127 have no key (k_ok_next stays false)
   constexpr int kVChunks = (kChunks + 1) / 2;
   uint4 k_raw[kChunks], v_raw[kVChunks];
   bool k_ok_next = false;
   auto prefetch = [&](int blk) {
     const int kp = ks + blk * kBlockKeys + key;
-    k_ok_next = blk < n_blocks && kp < ke;
+    k_ok_next = blk < n_blocks && kp < ke && key < kBlockKeys;
     if (k_ok_next) {
       const int32_t krow = __ldg(p.order + kp);
       const uint4 *ksrc = reinterpret_cast<const uint4 *>(p.k + (int64_t)krow * p.ld + h * DP);
@@ -182,7 +185,7 @@ __global__ void __launch_bounds__(kThreads, DP <= 32 ? 4 : 3) window_attention_t
       tc_fence_after();
     }
     // ---- registers -> shared memory: K normalised (K-major), V transposed ----
-    {
+    if (key < kBlockKeys) {
       float f[DP];
       float ss = 0.0f;
 #pragma unroll
@@ -263,10 +266,12 @@ __global__ void __launch_bounds__(kThreads, DP <= 32 ? 4 : 3) window_attention_t
       tmem_ld_wait();
 #pragma unroll
       for (int i = 0; i < 32; ++i) s[i] = __uint_as_float(r[i]);
-      tmem_ld32(tmem_row + 32, r);
-      tmem_ld_wait();
+      if constexpr (kBlockKeys == 64) {
+        tmem_ld32(tmem_row + 32, r);
+        tmem_ld_wait();
 #pragma unroll
-      for (int i = 0; i < 32; ++i) s[32 + i] = __uint_as_float(r[i]);
+        for (int i = 0; i < 32; ++i) s[32 + i] = __uint_as_float(r[i]);
+      }
     }
     float m_new = m_run;                                           // maxima are kept in raw (unscaled) score units
 #pragma unroll
@@ -377,9 +382,12 @@ extern "C" int os3d_window_attention_bf16_tc(const void *q, const void *k, const
   p.heads = heads;
   dim3 grid((unsigned)(cdiv(m, attn_tc::kTileQ) * heads));
   cudaStream_t st = (cudaStream_t)stream;
-  if (dp == 16) attn_tc::window_attention_tc_kernel<16><<<grid, attn_tc::kThreads, 0, st>>>(p);
-  else if (dp == 32) attn_tc::window_attention_tc_kernel<32><<<grid, attn_tc::kThreads, 0, st>>>(p);
-  else attn_tc::window_attention_tc_kernel<48><<<grid, attn_tc::kThreads, 0, st>>>(p);
+  const char *e = getenv("OS3D_ATTN_KB");                       // tuning override: keys per block for dp = 16
+  const bool kb32 = e ? atoi(e) == 32 : true;
+  if (dp == 16 && kb32) attn_tc::window_attention_tc_kernel<16, 32><<<grid, attn_tc::kThreads, 0, st>>>(p);
+  else if (dp == 16) attn_tc::window_attention_tc_kernel<16, 64><<<grid, attn_tc::kThreads, 0, st>>>(p);
+  else if (dp == 32) attn_tc::window_attention_tc_kernel<32, 64><<<grid, attn_tc::kThreads, 0, st>>>(p);
+  else attn_tc::window_attention_tc_kernel<48, 64><<<grid, attn_tc::kThreads, 0, st>>>(p);
   OS3D_LAUNCH_CHECK();
   return 0;
 }

@@ -80,6 +80,62 @@ def kernel_map_tiles(nbr):
     return hit
 
 
+class _SparseConvFunction(torch.autograd.Function):
+    """Differentiable sparse convolution (conv + bias, no fused epilogue) for training.
+
+    forward : out[r] = b + sum_k in[nbr[r, k]] W[k]^T                          -- the forward kernels
+    dgrad   : din[j] = sum_k dout[nbr_bwd[j, k]] Wb[k]^T                       -- the SAME kernels on the transposed
+              problem: the output-stationary map of the transposed conv is the strided pair's other table
+              (SparseConv3d <-> SparseInverseConv3d) or, for a submanifold conv, the map itself with the offsets
+              mirrored (nbr[r, k] = j  <=>  nbr[j, 26 - k] = r); Wb[k] = W[k]^T (W[26 - k]^T when mirrored).
+    wgrad   : dW[:, k, :] = dout^T . in[nbr[:, k]]   (rows without a neighbour contribute zero) -- 27 library GEMMs
+              over masked gathers; a native gathered-wgrad kernel is listed under "next" in DESIGN.md.
+    """
+
+    @staticmethod
+    def forward(ctx, features, weight, bias, nbr, nbr_bwd, mirror, m_in, packed_cache):
+        out = sparse_conv_forward(features.detach(), nbr, weight.detach(), None if bias is None else bias.detach(),
+                                  packed_cache)
+        ctx.save_for_backward(features, weight)
+        ctx.nbr, ctx.nbr_bwd, ctx.mirror, ctx.has_bias, ctx.m_in = nbr, nbr_bwd, mirror, bias is not None, m_in
+        return out
+
+    @staticmethod
+    def backward(ctx, gout):
+        features, weight = ctx.saved_tensors
+        gout = gout.contiguous()
+        cout, cin = weight.shape[0], weight.shape[-1]
+        gin = gw = gb = None
+        if ctx.needs_input_grad[0]:
+            w3 = weight.detach().reshape(cout, 27, cin)
+            if ctx.mirror:
+                w3 = w3.flip(1)
+            wb = w3.permute(2, 1, 0).contiguous()                       # [cin, 27, cout]: a conv weight with the roles swapped
+            pad = (-cin) % 16 if gout.dtype == torch.bfloat16 else 0    # tensor-core kernel: output channels % 16
+            if pad:
+                wb = F.pad(wb, (0, 0, 0, 0, 0, pad))
+            parts = []
+            n_out = cin + pad
+            step = n_out if n_out <= 512 else n_out // ((n_out + 511) // 512)
+            for off in range(0, n_out, step):
+                parts.append(sparse_conv_forward(gout, ctx.nbr_bwd, wb[off:off + step].reshape(-1, 3, 3, 3, cout), None,
+                                                 _PackedWeights()))
+            gin = parts[0] if len(parts) == 1 else torch.cat(parts, dim=1)
+            if pad:
+                gin = gin[:, :cin].contiguous()
+        if ctx.needs_input_grad[1]:
+            gw = torch.empty((cout, 27, cin), dtype=torch.float32, device=weight.device)
+            g_t = gout.t().contiguous()
+            for k in range(27):
+                idx = ctx.nbr[:, k].long()
+                xk = features.detach()[idx.clamp(min=0)] * (idx >= 0).unsqueeze(1).to(features.dtype)
+                gw[:, k, :] = torch.mm(g_t, xk).float()
+            gw = gw.reshape(weight.shape).to(weight.dtype)
+        if ctx.has_bias and ctx.needs_input_grad[2]:
+            gb = gout.float().sum(dim=0)
+        return gin, gw, gb, None, None, None, None, None
+
+
 class _PackedWeights(object):
     """Kernel-layout copies of a conv weight, rebuilt when the parameter changes (version counter / storage)."""
 
@@ -134,16 +190,17 @@ class _SparseConvBase(SparseModule):
         return (f'{self.in_channels}, {self.out_channels}, kernel_size={self.kernel_size}, stride={self.stride}, '
                 f'padding={self.padding}, bias={self.bias is not None}, indice_key={self.indice_key}')
 
-    def _check_grad(self, x):
-        if torch.is_grad_enabled() and (x.features.requires_grad or self.weight.requires_grad):
-            raise NotImplementedError('sparse conv backward is not built yet (DESIGN.md, "Not yet built"); '
-                                      'run the forward under torch.no_grad()')
-
-    # subclasses: table(x) -> (nbr, out SparseConvTensor prototype)
+    # subclasses: _table(x) -> (nbr, out SparseConvTensor prototype); _table_bwd(x) -> (map of the transposed conv, mirror)
     def forward(self, x, scale=None, shift=None, residual=None, relu=False):
-        self._check_grad(x)
         nbr, out_proto = self._table(x)
-        feats = sparse_conv_forward(x.features, nbr, self.weight, self.bias, self._packed, scale, shift, residual, relu)
+        if torch.is_grad_enabled() and (x.features.requires_grad or self.weight.requires_grad):
+            if scale is not None or residual is not None or relu:
+                raise RuntimeError('the fused conv epilogue is an inference path; training runs conv, BatchNorm, ReLU separately')
+            nbr_bwd, mirror = self._table_bwd(x)
+            feats = _SparseConvFunction.apply(x.features, self.weight, self.bias, nbr, nbr_bwd, mirror, x.features.shape[0],
+                                              self._packed)
+        else:
+            feats = sparse_conv_forward(x.features, nbr, self.weight, self.bias, self._packed, scale, shift, residual, relu)
         return out_proto(feats)
 
 
@@ -158,7 +215,11 @@ class SubMConv3d(_SparseConvBase):
             rb = build_subm_rulebook(x)
             if self.indice_key is not None:
                 x.indice_dict[self.indice_key] = rb
+        self._last_rb = rb
         return rb.nbr, x.replace_feature
+
+    def _table_bwd(self, x):
+        return self._last_rb.nbr, True          # the submanifold map is its own transpose with the offsets mirrored
 
 
 class SparseConv3d(_SparseConvBase):
@@ -174,8 +235,12 @@ class SparseConv3d(_SparseConvBase):
             rb = build_strided_rulebook(x)
             if self.indice_key is not None:
                 x.indice_dict[self.indice_key] = rb
+        self._last_rb = rb
         return rb.fwd_nbr, lambda f: SparseConvTensor(f, rb.out_indices, rb.out_shape, x.batch_size, x.indice_dict,
                                                       x._site_table)
+
+    def _table_bwd(self, x):
+        return self._last_rb.inv_nbr, False
 
 
 class SparseInverseConv3d(_SparseConvBase):
@@ -190,6 +255,9 @@ class SparseInverseConv3d(_SparseConvBase):
             raise RuntimeError('SparseInverseConv3d input does not live on the sites that SparseConv3d produced')
         return rb.inv_nbr, lambda f: SparseConvTensor(f, rb.in_indices, rb.in_shape, x.batch_size, x.indice_dict,
                                                       x._site_table)
+
+    def _table_bwd(self, x):
+        return x.find_indice_pair(self.indice_key).fwd_nbr, False
 
 
 def bn_scale_shift(bn, conv_bias=None):

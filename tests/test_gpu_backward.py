@@ -1,0 +1,71 @@
+"""Backward of the hot path (BASELINE config 5): gradients of the CUDA ops against torch autograd through the CPU
+oracle's restatement of the same op, on the same operands.  fp32: rel 1e-4; bf16: rel 2e-2 (north star)."""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def _sites(rng, batch, shape, n):
+    z, y, x = shape
+    lin = rng.choice(batch * z * y * x, size=n, replace=False)
+    b, r = np.divmod(lin, z * y * x)
+    zz, r = np.divmod(r, y * x)
+    yy, xx = np.divmod(r, x)
+    return np.stack([b, zz, yy, xx], axis=1).astype(np.int32)
+
+
+def _rel(a, b):
+    return float((a.double().cpu() - b.double()).abs().max() / (b.double().abs().max() + 1e-30))
+
+
+@pytest.mark.parametrize('kind,cin,cout,dtype', [('subm', 16, 32, torch.float32), ('subm', 48, 48, torch.bfloat16),
+                                                ('strided', 32, 48, torch.float32), ('strided', 48, 96, torch.bfloat16),
+                                                ('inverse', 48, 32, torch.float32), ('inverse', 96, 48, torch.bfloat16),
+                                                ('subm', 40, 48, torch.bfloat16)])
+def test_sparse_conv_backward_matches_oracle_autograd(kind, cin, cout, dtype):
+    from openseg3d_b200 import spconv
+    from oracle import oracle
+    rng = np.random.default_rng(cin + cout)
+    torch.manual_seed(cin * 7 + cout)
+    shape = (10, 30, 30)
+    idx = _sites(rng, 2, shape, 2500)
+    bf16 = dtype == torch.bfloat16
+    rnd = (lambda t: t.bfloat16().float()) if bf16 else (lambda t: t)
+    x = spconv.SparseConvTensor(torch.zeros(idx.shape[0], 1).cuda(), torch.from_numpy(idx).cuda(), shape, 2)
+    if kind == 'subm':
+        conv = spconv.SubMConv3d(cin, cout, 3, padding=1, bias=True, indice_key='k').cuda()
+        nbr, _ = oracle.subm_map(idx, shape)
+        m_in = idx.shape[0]
+    else:
+        down = spconv.SparseConv3d(8, 8, 3, stride=2, padding=1, bias=False, indice_key='s').cuda()
+        with torch.no_grad():
+            y0 = down(x.replace_feature(torch.zeros(idx.shape[0], 8).cuda()))          # builds the strided rulebook
+        _, _, fwd, inv, _ = oracle.strided_map(idx, shape)
+        if kind == 'strided':
+            conv = spconv.SparseConv3d(cin, cout, 3, stride=2, padding=1, bias=False, indice_key='s').cuda()
+            nbr, m_in = fwd, idx.shape[0]
+        else:
+            conv = spconv.SparseInverseConv3d(cin, cout, 3, bias=False, indice_key='s').cuda()
+            nbr, m_in = inv, y0.features.shape[0]
+            x = y0
+    with torch.no_grad():
+        conv.weight.copy_(rnd(conv.weight))
+    feats = rnd(torch.randn(m_in, cin))
+    f_gpu = feats.to(dtype).cuda().requires_grad_(True)
+    out = conv(x.replace_feature(f_gpu)).features
+    gout = rnd(torch.randn(out.shape))
+    out.backward(gout.to(dtype).cuda())
+
+    f_ref = feats.double().requires_grad_(True)
+    w_ref = conv.weight.detach().cpu().double().requires_grad_(True)
+    b_ref = conv.bias.detach().cpu().double().requires_grad_(True) if conv.bias is not None else None
+    ref = oracle.sparse_conv(f_ref, nbr, w_ref, b_ref)
+    ref.backward(gout.double())
+    tol = 2e-2 if bf16 else 1e-4
+    assert _rel(out.detach().float(), ref.detach()) < tol
+    assert _rel(f_gpu.grad.float(), f_ref.grad) < tol, _rel(f_gpu.grad.float(), f_ref.grad)
+    assert _rel(conv.weight.grad, w_ref.grad) < tol, _rel(conv.weight.grad, w_ref.grad)
+    if b_ref is not None:
+        assert _rel(conv.bias.grad, b_ref.grad) < tol
