@@ -215,11 +215,24 @@ int os3d_qk_normalize(void *q, void *k, int64_t ld, int64_t m, int c, int heads,
  * tau: device f32[1];  lvl_tokens: host int[4] (max_tokens per batching level, sizes the work decomposition).
  * out [m, c] in the original voxel order.  elem_size 4 (f32) or 2 (bf16).
  * replaces: flat2window + CosineMultiheadAttention core + window2flat (swformer_utils.py:34-85,
- *           seg3d/models/layers/cosine_msa.py:115-177, point_transformer_layer.py:233-258). */
+ *           seg3d/models/layers/cosine_msa.py:115-177, point_transformer_layer.py:233-258).
+ * drop_p > 0 (training): attention dropout on the softmax weights (cosine_msa.py:173-174) with a keep-mask hashed from
+ * (seed, head, query row, key row) -- reproducible from the seed, regenerated by the backward. */
 int os3d_window_attention(const void *q, const void *k, const void *v, int64_t ld, int64_t ldv, int64_t m, int c, int heads,
                           const int32_t *order, const int32_t *seg_start, const int32_t *seg_len,
                           const int32_t *level_info, const int *lvl_tokens, const float *tau, float tau_min,
-                          int elem_size, void *out, void *stream);
+                          float drop_p, uint64_t seed, int elem_size, void *out, void *stream);
+
+/* Backward of os3d_window_attention.  q, k (normalised), v, o (the forward's output), go (gradient of o), gq, gk, gv:
+ * [m, c] rows of pitch c.  stats: scratch f32 [m * heads * 3].  g_inv_tau: device f32[1], zeroed by the caller, receives
+ * d loss / d (1 / max(tau, tau_min)).  Two kernels: query-stationary (row statistics, gq, g_inv_tau) and key-stationary
+ * (gk, gv) -- no atomics on the row gradients.
+ * replaces: autograd through torch.bmm / softmax / dropout of _scaled_cosine_attention (cosine_msa.py:152-176). */
+int os3d_window_attention_bwd(const void *q, const void *k, const void *v, const void *o, const void *go, int64_t m, int c,
+                              int heads, const int32_t *order, const int32_t *seg_start, const int32_t *seg_len,
+                              const int32_t *level_info, const int *lvl_tokens, const float *tau, float tau_min,
+                              float drop_p, uint64_t seed, int elem_size, float *stats, void *gq, void *gk, void *gv,
+                              float *g_inv_tau, void *stream);
 
 /* The same attention on the tcgen05 tensor cores (bf16): QK^T and PV as UMMA tiles with TMEM accumulators, q / k
  * normalisation folded into the gather (do NOT call os3d_qk_normalize first).  Head-padded layout: head h occupies

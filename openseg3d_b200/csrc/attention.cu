@@ -84,6 +84,16 @@ __global__ void qk_normalize_kernel(T *__restrict__ q, T *__restrict__ k, int64_
   }
 }
 
+// Attention dropout (training; cosine_msa.py:173-174): keep-mask of weight (head, query row, key row) from a
+// counter-based hash of (seed, head, rows), so forward and backward regenerate the same mask without storing it.  Not
+// torch's Philox stream: a run is reproducible from its seed, not bit-identical to the reference's dropout.
+__device__ __forceinline__ float drop_keep(uint64_t seed, int h, int32_t qrow, int32_t krow, float drop_p, float keep_scale) {
+  if (drop_p <= 0.0f) return 1.0f;
+  const uint64_t x = mix64(seed ^ ((uint64_t)(uint32_t)qrow << 32 | (uint32_t)krow) ^ ((uint64_t)h * 0x9e3779b97f4a7c15ULL));
+  const float u = (float)(x >> 40) * (1.0f / 16777216.0f);          // 24 random bits -> [0, 1)
+  return u >= drop_p ? keep_scale : 0.0f;
+}
+
 struct AttnLevels {
   int chunks[OS3D_MAX_LEVELS];  // ceil(max_tokens / 32) per level
 };
@@ -96,12 +106,14 @@ __global__ void __launch_bounds__(128) window_attention_kernel(const T *__restri
                                                                 const int32_t *__restrict__ seg_len,
                                                                 const int32_t *__restrict__ level_info,
                                                                 AttnLevels lv, const float *__restrict__ tau,
-                                                                float tau_min, T *__restrict__ out, int64_t ldo) {
+                                                                float tau_min, float drop_p, uint64_t seed,
+                                                                T *__restrict__ out, int64_t ldo) {
   const int lane = threadIdx.x & 31;
   const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int64_t n_warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
   // softmax in base 2: scores * log2(e) / max(tau, tau_min)
   const float scale = 1.4426950408889634f / fmaxf(__ldg(tau), tau_min);
+  const float keep_scale = drop_p > 0.0f ? 1.0f / (1.0f - drop_p) : 1.0f;
 
   int64_t items_before = 0;
   for (int lvl = OS3D_MAX_LEVELS - 1; lvl >= 0; --lvl) {  // heaviest windows first
@@ -148,9 +160,10 @@ __global__ void __launch_bounds__(128) window_attention_kernel(const T *__restri
             mx = s;
           }
           const float p = exp2f(s - mx);
-          sum += p;
+          sum += p;                                                     // the softmax denominator ignores dropout
+          const float pd = p * drop_keep(seed, h, qrow, krow, drop_p, keep_scale);
 #pragma unroll
-          for (int i = 0; i < D; ++i) acc[i] = fmaf(p, vr[i], acc[i]);
+          for (int i = 0; i < D; ++i) acc[i] = fmaf(pd, vr[i], acc[i]);
         }
       }
       if (active) {
@@ -169,8 +182,8 @@ __global__ void __launch_bounds__(128) window_attention_kernel(const T *__restri
 template <typename T>
 static int launch_attention(const T *q, const T *k, const T *v, int64_t ld, int64_t ldv, int64_t m, int c, int heads,
                             const int32_t *order, const int32_t *seg_start, const int32_t *seg_len,
-                            const int32_t *level_info, const int *lvl_tokens, const float *tau, float tau_min, T *out,
-                            cudaStream_t st) {
+                            const int32_t *level_info, const int *lvl_tokens, const float *tau, float tau_min,
+                            float drop_p, uint64_t seed, T *out, cudaStream_t st) {
   const int d = c / heads;
   AttnLevels lv;
   for (int l = 0; l < OS3D_MAX_LEVELS; ++l) lv.chunks[l] = (lvl_tokens[l] + 31) / 32;
@@ -181,7 +194,7 @@ static int launch_attention(const T *q, const T *k, const T *v, int64_t ld, int6
 #define OS3D_ATTN_CASE(DD)                                                                                          \
   case DD:                                                                                                          \
     window_attention_kernel<T, DD><<<blocks, 128, 0, st>>>(q, k, v, ld, ldv, heads, order, seg_start, seg_len, level_info, \
-                                                           lv, tau, tau_min, out, (int64_t)c);                      \
+                                                           lv, tau, tau_min, drop_p, seed, out, (int64_t)c);        \
     break;
   switch (d) {
     OS3D_ATTN_CASE(3)
@@ -196,6 +209,184 @@ static int launch_attention(const T *q, const T *k, const T *v, int64_t ld, int6
       return OS3D_ERR_BAD_ARG;
   }
 #undef OS3D_ATTN_CASE
+  return 0;
+}
+
+// ---- backward ----------------------------------------------------------------------------------------------------
+// With z_ij = (q_i . k_j) / tau', P = softmax_j(z), P' = dropout(P), O = P' V:
+//   D_i   = dO_i . O_i  (= sum_j P_ij dP_ij),   dP_ij = keep_ij (dO_i . v_j),   dz_ij = P_ij (dP_ij - D_i)
+//   dq_i  = sum_j dz_ij k_j / tau'      dk_j = sum_i dz_ij q_i / tau'      dv_j = sum_i P'_ij dO_i
+//   d(1/tau') = sum_ij dz_ij (q_i . k_j)
+// Pass A (lane = query): row statistics (max, sum, D) into `stats`, dq, the 1/tau' gradient.
+// Pass B (lane = key)  : dk, dv accumulate in the key lane's registers while the window's queries are broadcast --
+//                        no cross-lane reductions, no atomics on dk / dv.
+template <typename T, int D>
+__device__ __forceinline__ void store_slice(T *p, const float *v) {
+#pragma unroll
+  for (int i = 0; i < D; ++i) {
+    if constexpr (sizeof(T) == 4) p[i] = v[i]; else p[i] = __float2bfloat16(v[i]);
+  }
+}
+
+template <typename T, int D, int PASS>
+__global__ void __launch_bounds__(128) window_attention_bwd_kernel(
+    const T *__restrict__ q, const T *__restrict__ k, const T *__restrict__ v, const T *__restrict__ o,
+    const T *__restrict__ go, int64_t ld, int heads, const int32_t *__restrict__ order,
+    const int32_t *__restrict__ seg_start, const int32_t *__restrict__ seg_len, const int32_t *__restrict__ level_info,
+    AttnLevels lv, const float *__restrict__ tau, float tau_min, float drop_p, uint64_t seed, float *__restrict__ stats,
+    T *__restrict__ gq, T *__restrict__ gk, T *__restrict__ gv, float *__restrict__ g_inv_tau) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int64_t n_warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  const float inv_tau = 1.0f / fmaxf(__ldg(tau), tau_min);
+  const float scale2 = 1.4426950408889634f * inv_tau;
+  const float keep_scale = drop_p > 0.0f ? 1.0f / (1.0f - drop_p) : 1.0f;
+  float g_scale_acc = 0.0f;
+
+  int64_t items_before = 0;
+  for (int lvl = OS3D_MAX_LEVELS - 1; lvl >= 0; --lvl) {
+    const int n_windows = __ldg(level_info + lvl);
+    const int first = __ldg(level_info + 4 + lvl);
+    const int chunks = lv.chunks[lvl];
+    const int64_t items = (int64_t)n_windows * heads * chunks;
+    int64_t it = warp - (items_before % n_warps);
+    if (it < 0) it += n_warps;
+    for (; it < items; it += n_warps) {
+      const int chunk = (int)(it % chunks);
+      const int h = (int)((it / chunks) % heads);
+      const int win = first + (int)(it / ((int64_t)chunks * heads));
+      const int n = __ldg(seg_len + win);
+      if (chunk * 32 >= n) continue;
+      const int32_t *seg = order + __ldg(seg_start + win);
+      const int mi = chunk * 32 + lane;                 // this lane's query (pass A) / key (pass B) inside the window
+      const bool active = mi < n;
+      const int32_t myrow = __ldg(seg + (active ? mi : 0));
+      if constexpr (PASS == 0) {
+        float qr[D], gor[D], acc[D];
+        load_slice<T, D>(q + (int64_t)myrow * ld + h * D, qr);
+        load_slice<T, D>(go + (int64_t)myrow * ld + h * D, gor);
+        float dsum = 0.0f;
+        {
+          float orow[D];
+          load_slice<T, D>(o + (int64_t)myrow * ld + h * D, orow);
+#pragma unroll
+          for (int i = 0; i < D; ++i) { dsum = fmaf(gor[i], orow[i], dsum); acc[i] = 0.0f; }
+        }
+        float mx = -INFINITY, sum = 0.0f;
+        for (int j0 = 0; j0 < n; j0 += 32) {            // row statistics
+          const int32_t my_key = j0 + lane < n ? __ldg(seg + j0 + lane) : 0;
+          const int jn = min(32, n - j0);
+          for (int jj = 0; jj < jn; ++jj) {
+            const int32_t krow = __shfl_sync(0xffffffffu, my_key, jj);
+            float kr[D];
+            load_slice<T, D>(k + (int64_t)krow * ld + h * D, kr);
+            float s = 0.0f;
+#pragma unroll
+            for (int i = 0; i < D; ++i) s = fmaf(qr[i], kr[i], s);
+            s *= scale2;
+            const float mn = fmaxf(mx, s);
+            sum = sum * exp2f(mx - mn) + exp2f(s - mn);
+            mx = mn;
+          }
+        }
+        const float inv_l = 1.0f / sum;
+        for (int j0 = 0; j0 < n; j0 += 32) {            // dq, d(1/tau')
+          const int32_t my_key = j0 + lane < n ? __ldg(seg + j0 + lane) : 0;
+          const int jn = min(32, n - j0);
+          for (int jj = 0; jj < jn; ++jj) {
+            const int32_t krow = __shfl_sync(0xffffffffu, my_key, jj);
+            float kr[D], vr[D];
+            load_slice<T, D>(k + (int64_t)krow * ld + h * D, kr);
+            load_slice<T, D>(v + (int64_t)krow * ld + h * D, vr);
+            float s = 0.0f, dp = 0.0f;
+#pragma unroll
+            for (int i = 0; i < D; ++i) { s = fmaf(qr[i], kr[i], s); dp = fmaf(gor[i], vr[i], dp); }
+            const float p = exp2f(s * scale2 - mx) * inv_l;
+            const float dz = p * (dp * drop_keep(seed, h, myrow, krow, drop_p, keep_scale) - dsum);
+            if (active) g_scale_acc = fmaf(dz, s, g_scale_acc);
+            const float w = dz * inv_tau;
+#pragma unroll
+            for (int i = 0; i < D; ++i) acc[i] = fmaf(w, kr[i], acc[i]);
+          }
+        }
+        if (active) {
+          store_slice<T, D>(gq + (int64_t)myrow * ld + h * D, acc);
+          float *st = stats + ((int64_t)myrow * heads + h) * 3;
+          st[0] = mx; st[1] = inv_l; st[2] = dsum;
+        }
+      } else {
+        float kr[D], vr[D], dk[D], dv[D];
+        load_slice<T, D>(k + (int64_t)myrow * ld + h * D, kr);
+        load_slice<T, D>(v + (int64_t)myrow * ld + h * D, vr);
+#pragma unroll
+        for (int i = 0; i < D; ++i) { dk[i] = 0.0f; dv[i] = 0.0f; }
+        for (int i0 = 0; i0 < n; i0 += 32) {
+          const int32_t my_q = i0 + lane < n ? __ldg(seg + i0 + lane) : 0;
+          const int in = min(32, n - i0);
+          for (int ii = 0; ii < in; ++ii) {
+            const int32_t qrow = __shfl_sync(0xffffffffu, my_q, ii);
+            float qr[D], gor[D];
+            load_slice<T, D>(q + (int64_t)qrow * ld + h * D, qr);
+            load_slice<T, D>(go + (int64_t)qrow * ld + h * D, gor);
+            const float *st = stats + ((int64_t)qrow * heads + h) * 3;
+            const float mx = __ldg(st), inv_l = __ldg(st + 1), dsum = __ldg(st + 2);
+            float s = 0.0f, dp = 0.0f;
+#pragma unroll
+            for (int i = 0; i < D; ++i) { s = fmaf(qr[i], kr[i], s); dp = fmaf(gor[i], vr[i], dp); }
+            const float p = exp2f(s * scale2 - mx) * inv_l;
+            const float keep = drop_keep(seed, h, qrow, myrow, drop_p, keep_scale);
+            const float w = p * (dp * keep - dsum) * inv_tau;
+            const float pk = p * keep;
+#pragma unroll
+            for (int i = 0; i < D; ++i) { dk[i] = fmaf(w, qr[i], dk[i]); dv[i] = fmaf(pk, gor[i], dv[i]); }
+          }
+        }
+        if (active) {
+          store_slice<T, D>(gk + (int64_t)myrow * ld + h * D, dk);
+          store_slice<T, D>(gv + (int64_t)myrow * ld + h * D, dv);
+        }
+      }
+    }
+    items_before += items;
+  }
+  if constexpr (PASS == 0) {
+#pragma unroll
+    for (int o2 = 16; o2 > 0; o2 >>= 1) g_scale_acc += __shfl_xor_sync(0xffffffffu, g_scale_acc, o2);
+    if (lane == 0 && g_scale_acc != 0.0f) atomicAdd(g_inv_tau, g_scale_acc);
+  }
+}
+
+template <typename T>
+static int launch_attention_bwd(const T *q, const T *k, const T *v, const T *o, const T *go, int64_t m, int c, int heads,
+                                const int32_t *order, const int32_t *seg_start, const int32_t *seg_len,
+                                const int32_t *level_info, const int *lvl_tokens, const float *tau, float tau_min,
+                                float drop_p, uint64_t seed, float *stats, T *gq, T *gk, T *gv, float *g_inv_tau,
+                                cudaStream_t st) {
+  const int d = c / heads;
+  AttnLevels lv;
+  for (int l = 0; l < OS3D_MAX_LEVELS; ++l) lv.chunks[l] = (lvl_tokens[l] + 31) / 32;
+  const int64_t want_warps = (m / 4 + 1) * heads;
+  const unsigned blocks = (unsigned)max((int64_t)1, min((int64_t)148 * 16, cdiv(want_warps, 4)));
+#define OS3D_ATTN_BWD_CASE(DD)                                                                                          \
+  case DD:                                                                                                              \
+    window_attention_bwd_kernel<T, DD, 0><<<blocks, 128, 0, st>>>(q, k, v, o, go, (int64_t)c, heads, order, seg_start,  \
+        seg_len, level_info, lv, tau, tau_min, drop_p, seed, stats, gq, gk, gv, g_inv_tau);                             \
+    window_attention_bwd_kernel<T, DD, 1><<<blocks, 128, 0, st>>>(q, k, v, o, go, (int64_t)c, heads, order, seg_start,  \
+        seg_len, level_info, lv, tau, tau_min, drop_p, seed, stats, gq, gk, gv, g_inv_tau);                             \
+    break;
+  switch (d) {
+    OS3D_ATTN_BWD_CASE(3)
+    OS3D_ATTN_BWD_CASE(6)
+    OS3D_ATTN_BWD_CASE(12)
+    OS3D_ATTN_BWD_CASE(16)
+    OS3D_ATTN_BWD_CASE(24)
+    OS3D_ATTN_BWD_CASE(32)
+    OS3D_ATTN_BWD_CASE(48)
+    OS3D_ATTN_BWD_CASE(64)
+    default:
+      return OS3D_ERR_BAD_ARG;
+  }
+#undef OS3D_ATTN_BWD_CASE
   return 0;
 }
 
@@ -221,17 +412,43 @@ extern "C" int os3d_qk_normalize(void *q, void *k, int64_t ld, int64_t m, int c,
 extern "C" int os3d_window_attention(const void *q, const void *k, const void *v, int64_t ld, int64_t ldv, int64_t m, int c,
                                      int heads, const int32_t *order, const int32_t *seg_start, const int32_t *seg_len,
                                      const int32_t *level_info, const int *lvl_tokens, const float *tau, float tau_min,
-                                     int elem_size, void *out, void *stream) {
+                                     float drop_p, uint64_t seed, int elem_size, void *out, void *stream) {
   if (m == 0) return 0;
-  if (heads <= 0 || c % heads) return OS3D_ERR_BAD_ARG;
+  if (heads <= 0 || c % heads || drop_p < 0.0f || drop_p >= 1.0f) return OS3D_ERR_BAD_ARG;
   int rc;
   if (elem_size == 4)
     rc = launch_attention<float>((const float *)q, (const float *)k, (const float *)v, ld, ldv, m, c, heads, order, seg_start,
-                                 seg_len, level_info, lvl_tokens, tau, tau_min, (float *)out, (cudaStream_t)stream);
+                                 seg_len, level_info, lvl_tokens, tau, tau_min, drop_p, seed, (float *)out, (cudaStream_t)stream);
   else if (elem_size == 2)
     rc = launch_attention<__nv_bfloat16>((const __nv_bfloat16 *)q, (const __nv_bfloat16 *)k, (const __nv_bfloat16 *)v, ld,
                                          ldv, m, c, heads, order, seg_start, seg_len, level_info, lvl_tokens, tau, tau_min,
-                                         (__nv_bfloat16 *)out, (cudaStream_t)stream);
+                                         drop_p, seed, (__nv_bfloat16 *)out, (cudaStream_t)stream);
+  else
+    return OS3D_ERR_BAD_ARG;
+  if (rc) return rc;
+  OS3D_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int os3d_window_attention_bwd(const void *q, const void *k, const void *v, const void *o, const void *go,
+                                         int64_t m, int c, int heads, const int32_t *order, const int32_t *seg_start,
+                                         const int32_t *seg_len, const int32_t *level_info, const int *lvl_tokens,
+                                         const float *tau, float tau_min, float drop_p, uint64_t seed, int elem_size,
+                                         float *stats, void *gq, void *gk, void *gv, float *g_inv_tau, void *stream) {
+  if (m == 0) return 0;
+  if (heads <= 0 || c % heads || drop_p < 0.0f || drop_p >= 1.0f) return OS3D_ERR_BAD_ARG;
+  int rc;
+  if (elem_size == 4)
+    rc = launch_attention_bwd<float>((const float *)q, (const float *)k, (const float *)v, (const float *)o,
+                                     (const float *)go, m, c, heads, order, seg_start, seg_len, level_info, lvl_tokens, tau,
+                                     tau_min, drop_p, seed, stats, (float *)gq, (float *)gk, (float *)gv, g_inv_tau,
+                                     (cudaStream_t)stream);
+  else if (elem_size == 2)
+    rc = launch_attention_bwd<__nv_bfloat16>((const __nv_bfloat16 *)q, (const __nv_bfloat16 *)k, (const __nv_bfloat16 *)v,
+                                             (const __nv_bfloat16 *)o, (const __nv_bfloat16 *)go, m, c, heads, order,
+                                             seg_start, seg_len, level_info, lvl_tokens, tau, tau_min, drop_p, seed, stats,
+                                             (__nv_bfloat16 *)gq, (__nv_bfloat16 *)gk, (__nv_bfloat16 *)gv, g_inv_tau,
+                                             (cudaStream_t)stream);
   else
     return OS3D_ERR_BAD_ARG;
   if (rc) return rc;

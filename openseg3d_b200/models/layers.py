@@ -235,6 +235,41 @@ class SparseWindowPartitionLayer(nn.Module):
         return info
 
 
+class _WindowAttentionFunction(torch.autograd.Function):
+    """Differentiable variable-length cosine window attention (training path): forward = os3d_window_attention on
+    already-normalised q / k (the normalisation itself stays in torch so autograd covers it), backward =
+    os3d_window_attention_bwd.  Attention dropout uses a seed-hashed keep mask regenerated in the backward."""
+
+    @staticmethod
+    def forward(ctx, qn, kn, v, tau, tau_min, heads, seg, drop_p, seed):
+        m, c = qn.shape
+        qn, kn, v = qn.contiguous(), kn.contiguous(), v.contiguous()
+        out = torch.empty_like(qn)
+        tau32 = tau.detach().float().reshape(1).contiguous()
+        _lib.call('os3d_window_attention', qn, kn, v, c, c, m, c, heads, seg.order, seg.seg_start, seg.seg_len,
+                  seg.level_info, ctypes.byref(seg.lvl_tokens), tau32, float(tau_min), float(drop_p), int(seed),
+                  qn.element_size(), out)
+        ctx.save_for_backward(qn, kn, v, out, tau32)
+        ctx.args = (tau_min, heads, seg, drop_p, seed, tau.shape, tau.dtype)
+        return out
+
+    @staticmethod
+    def backward(ctx, gout):
+        qn, kn, v, out, tau32 = ctx.saved_tensors
+        tau_min, heads, seg, drop_p, seed, tau_shape, tau_dtype = ctx.args
+        m, c = qn.shape
+        gout = gout.contiguous()
+        gq, gk, gv = torch.empty_like(qn), torch.empty_like(kn), torch.empty_like(v)
+        stats = torch.empty(m * heads * 3, dtype=torch.float32, device=qn.device)
+        g_inv = torch.zeros(1, dtype=torch.float32, device=qn.device)
+        _lib.call('os3d_window_attention_bwd', qn, kn, v, out, gout, m, c, heads, seg.order, seg.seg_start, seg.seg_len,
+                  seg.level_info, ctypes.byref(seg.lvl_tokens), tau32, float(tau_min), float(drop_p), int(seed),
+                  qn.element_size(), stats, gq, gk, gv, g_inv)
+        # d(1 / max(tau, tau_min)) / d tau = -1 / tau^2 above the clamp, 0 below
+        gtau = torch.where(tau32 > tau_min, -g_inv / (tau32 * tau32), torch.zeros_like(g_inv))
+        return gq, gk, gv, gtau.reshape(tau_shape).to(tau_dtype), None, None, None, None, None
+
+
 class CosineMultiheadAttention(nn.MultiheadAttention):
     """Parameters identical to the reference subclass (cosine_msa.py:413-431): in_proj_weight / in_proj_bias /
     out_proj.{weight,bias} from nn.MultiheadAttention plus the shared temperature ``tau`` [1, 1, 1]."""
@@ -318,9 +353,9 @@ class CosineMultiheadAttention(nn.MultiheadAttention):
 
     def forward_segments(self, feat, pos_dict, seg):
         """feat: flat [M, C]; pos_dict: PosDict or None; seg: WindowSegments.  Returns [M, C]."""
-        if self.training and self.dropout > 0:
-            raise NotImplementedError('attention dropout (training) is not built yet')
         m, c = feat.shape
+        if torch.is_grad_enabled() and (feat.requires_grad or self.in_proj_weight.requires_grad):
+            return self._forward_train(feat, pos_dict, seg)
         if self.tensor_core_ok(feat):
             heads, o_c = self.attention_heads(feat, pos_dict, seg)
             return linear_bf16(heads, o_c)
@@ -335,8 +370,25 @@ class CosineMultiheadAttention(nn.MultiheadAttention):
         out = torch.empty((m, c), dtype=feat.dtype, device=feat.device)
         _lib.call('os3d_window_attention', qk, k_ptr, v, 2 * c, c, m, c, self.num_heads, seg.order, seg.seg_start,
                   seg.seg_len, seg.level_info, ctypes.byref(seg.lvl_tokens), self.tau.detach().float().reshape(1),
-                  float(self.tau_min), es, out)
+                  float(self.tau_min), 0.0, 0, es, out)
         return F.linear(out, w_out, b_out)
+
+    def _forward_train(self, feat, pos_dict, seg):
+        """Differentiable path (cosine_multi_head_attention_forward, cosine_msa.py:180-408): projections and the q / k
+        normalisation are torch ops (autograd), the attention core is _WindowAttentionFunction."""
+        m, c = feat.shape
+        h = self.num_heads
+        dt = feat.dtype
+        w_in, b_in = self.in_proj_weight.to(dt), self.in_proj_bias.to(dt)
+        qk_in = feat if pos_dict is None else feat + pos_dict['flat'].to(dt)
+        qk = F.linear(qk_in, w_in[:2 * c], b_in[:2 * c])
+        v = F.linear(feat, w_in[2 * c:], b_in[2 * c:])
+        qn = F.normalize(qk[:, :c].reshape(m, h, c // h).float(), dim=-1).reshape(m, c).to(dt)
+        kn = F.normalize(qk[:, c:].reshape(m, h, c // h).float(), dim=-1).reshape(m, c).to(dt)
+        drop_p = self.dropout if self.training else 0.0
+        seed = int(torch.randint(0, 2 ** 62, (1,)).item()) if drop_p > 0 else 0
+        out = _WindowAttentionFunction.apply(qn, kn, v, self.tau, self.tau_min, h, seg, drop_p, seed)
+        return F.linear(out, self.out_proj.weight.to(dt), self.out_proj.bias.to(dt))
 
 
 class WindowAttention(nn.Module):

@@ -69,3 +69,51 @@ def test_sparse_conv_backward_matches_oracle_autograd(kind, cin, cout, dtype):
     assert _rel(conv.weight.grad, w_ref.grad) < tol, _rel(conv.weight.grad, w_ref.grad)
     if b_ref is not None:
         assert _rel(conv.bias.grad, b_ref.grad) < tol
+
+
+@pytest.mark.parametrize('c,heads,dtype', [(24, 2, torch.float32), (48, 8, torch.float32), (96, 8, torch.bfloat16),
+                                           (192, 8, torch.float32)])
+def test_window_attention_backward_matches_oracle_autograd(c, heads, dtype):
+    """Gradients of WindowAttention (projections, normalisation, attention core, temperature) against torch autograd
+    through the oracle's padded-window restatement of cosine_msa.py on the same parameters."""
+    from openseg3d_b200 import spconv
+    from openseg3d_b200.models import SparseWindowPartitionLayer, WindowAttention
+    from openseg3d_b200.models.segmentors import default_batching_info
+    from oracle import oracle
+    rng = np.random.default_rng(c)
+    torch.manual_seed(c)
+    shape = (8, 40, 40)                                       # z, y, x
+    idx = _sites(rng, 2, shape, 1500)
+    binfo = default_batching_info()[0]
+    layer = SparseWindowPartitionLayer(binfo, (10, 10, 8), (shape[2], shape[1], shape[0]))
+    attn = WindowAttention(c, heads, 0.0).cuda()
+    bf16 = dtype == torch.bfloat16
+    rnd = (lambda t: t.bfloat16().float()) if bf16 else (lambda t: t)
+    with torch.no_grad():
+        attn.self_attn.tau.fill_(0.4)
+        for p in attn.parameters():
+            p.copy_(rnd(p))
+    feats = rnd(torch.randn(idx.shape[0], c))
+    x = spconv.SparseConvTensor(feats.to(dtype).cuda(), torch.from_numpy(idx).cuda(), shape, 2)
+    info = layer(x)
+    f_gpu = feats.to(dtype).cuda().requires_grad_(True)
+    out = attn(f_gpu, info['pos_dict_shift0'], info['flat2win_inds_shift0'], info['key_mask_shift0'])
+    gout = rnd(torch.randn(out.shape))
+    out.backward(gout.to(dtype).cuda())
+
+    # oracle: padded windows per batching level, torch ops in float64 on the CPU
+    sd = {k: v.detach().cpu().double().requires_grad_(True) for k, v in attn.self_attn.state_dict(keep_vars=True).items()}
+    part = oracle.partition(idx, (shape[2], shape[1], shape[0]), (10, 10, 8), binfo, c)
+    f_ref = feats.double().requires_grad_(True)
+    shift = part[0]
+    x3 = oracle.flat2window(f_ref, shift['inds'], binfo)
+    p3 = oracle.flat2window(torch.as_tensor(shift['pos_flat']).double(), shift['inds'], binfo)
+    o3 = {lvl: oracle.cosine_attention(x3[lvl], p3[lvl], shift['mask'][lvl], sd, heads) for lvl in x3}
+    ref = oracle.window2flat(o3, shift['inds'], idx.shape[0])
+    ref.backward(gout.double())
+    tol = 3e-2 if bf16 else 2e-4
+    assert _rel(out.detach().float(), ref.detach()) < tol
+    assert _rel(f_gpu.grad.float(), f_ref.grad) < tol, _rel(f_gpu.grad.float(), f_ref.grad)
+    for name in ('in_proj_weight', 'in_proj_bias', 'out_proj.weight', 'out_proj.bias', 'tau'):
+        g = dict(attn.self_attn.named_parameters())[name].grad
+        assert _rel(g, sd[name].grad) < tol, (name, _rel(g, sd[name].grad))
