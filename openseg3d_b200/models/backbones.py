@@ -57,7 +57,7 @@ class SparseBasicBlock(spconv.SparseModule):
         self.bn2 = norm_fn(planes)
 
     def forward(self, x):
-        if not self.training:        # inference: BN, residual add and ReLU live in the conv epilogues
+        if not self.training and not torch.is_grad_enabled():   # inference: BN, residual add and ReLU live in the conv epilogues
             s1, b1 = bn_scale_shift(self.bn1, self.conv1.bias)
             s2, b2 = bn_scale_shift(self.bn2, self.conv2.bias)
             out = self.conv1(x, scale=s1, shift=b1, relu=True)
@@ -98,7 +98,7 @@ class UpBlock(spconv.SparseModule):
     def forward(self, x_bottom, x_lateral):
         x_trans = self.transform(x_lateral)
         x = replace_feature(x_trans, torch.cat([x_bottom.features, x_trans.features], dim=1))
-        if not self.training:        # inference: BN + ReLU + channel_reduction(cat) + add in the bottleneck's epilogue
+        if not self.training and not torch.is_grad_enabled():   # inference: BN + ReLU + channel_reduction(cat) + add in the bottleneck's epilogue
             conv, bn = self.bottleneck[0], self.bottleneck[1]
             scale, shift = bn_scale_shift(bn, conv.bias)
             return self.out(conv(x, scale=scale, shift=shift, residual=x.features, relu=3))

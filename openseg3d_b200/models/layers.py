@@ -409,6 +409,8 @@ def _cast_like(mod, name, dtype):
     p = getattr(mod, name)
     if p is None or p.dtype == dtype:
         return p
+    if torch.is_grad_enabled() and p.requires_grad:
+        return p.to(dtype)                    # differentiable cast: the gradient reaches the fp32 parameter
     cache = mod.__dict__.setdefault('_os3d_cast', {})
     tag = (dtype, p._version, p.data_ptr())
     hit = cache.get(name)
@@ -489,7 +491,7 @@ class EncoderLayer(nn.Module):
 
     def forward(self, x, pos_dict, ind_dict, key_padding_mask_dict=None):
         mha = self.win_attn.self_attn
-        if not self.training and mha.tensor_core_ok(x) and isinstance(pos_dict, PosDict):
+        if not self.training and not torch.is_grad_enabled() and mha.tensor_core_ok(x) and isinstance(pos_dict, PosDict):
             # bf16 inference: the two projections that are followed by residual + LayerNorm run on the tcgen05 kernel
             # with that epilogue fused (os3d_linear_bf16): the [M, C] projection output never goes to HBM
             x = x.contiguous()
@@ -500,7 +502,7 @@ class EncoderLayer(nn.Module):
             return linear_bf16(h, cache.get('fc2', self.mlp.fc2.weight, self.mlp.fc2.bias, max_width=512), residual=x1,
                                ln=_ln_params(self.norm2))
         attn = self.win_attn(x, pos_dict, ind_dict, key_padding_mask_dict)
-        if self.training:
+        if self.training or torch.is_grad_enabled():
             x = x + self.drop_path(layer_norm_in(self.norm1, attn))
             return x + self.drop_path(layer_norm_in(self.norm2, self.mlp(x)))
         x = residual_layer_norm(self.norm1, attn, x)

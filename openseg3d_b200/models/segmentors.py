@@ -162,7 +162,7 @@ class Segformer(nn.Module):
             cur_points = points[cur_point_indices]
         else:
             cur_points = points
-        fold = not self.training                          # inference: BatchNorm folded, ReLU in the GEMM epilogue
+        fold = not self.training and not torch.is_grad_enabled()   # inference: BatchNorm folded, ReLU in the GEMM epilogue
         if fold:
             point_per_features = self._folded('point_encoder')(cur_points, self.compute_dtype)
         else:

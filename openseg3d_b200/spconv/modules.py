@@ -294,7 +294,7 @@ class SparseSequential(SparseModule):
         i = 0
         while i < len(mods):
             m = mods[i]
-            if isinstance(m, _SparseConvBase) and not self.training and i + 1 < len(mods) \
+            if isinstance(m, _SparseConvBase) and not self.training and not torch.is_grad_enabled() and i + 1 < len(mods) \
                     and isinstance(mods[i + 1], nn.BatchNorm1d) and isinstance(x, SparseConvTensor):
                 relu = i + 2 < len(mods) and isinstance(mods[i + 2], nn.ReLU)
                 scale, shift = bn_scale_shift(mods[i + 1], m.bias)

@@ -431,12 +431,16 @@ CLASSIFIER = [('lin', 0), ('bn', 1), ('relu', 2), ('lin', 4)]
 
 
 def segformer_forward(sd, points, voxel_size, pc_range, batching_info, window_shape, depths, multi_sweeps=False,
-                      stats=None):
-    """Raw collated points [sum N, 1+D] float32 (numpy) -> dict of torch tensors.  Eval mode."""
-    sd = {k: v.detach().float().cpu() for k, v in sd.items()}
+                      stats=None, differentiable=False):
+    """Raw collated points [sum N, 1+D] float32 (numpy) -> dict of torch tensors.  Eval mode.
+    differentiable=True: ``sd`` holds CPU leaf tensors (any float dtype) that are used as they are, so torch autograd
+    through this restatement is the gradient oracle of the backward tests."""
+    if not differentiable:
+        sd = {k: v.detach().float().cpu() for k, v in sd.items()}
+    dt = next(v.dtype for v in sd.values() if v.dtype.is_floating_point)
     coors, pvid = voxelize(points, voxel_size, pc_range, has_batch=True)
     pv = torch.from_numpy(pvid)
-    pts = torch.from_numpy(np.ascontiguousarray(points[:, 1:], np.float32))
+    pts = torch.from_numpy(np.ascontiguousarray(points[:, 1:], np.float32)).to(dt)
     bidx = torch.from_numpy(np.ascontiguousarray(points[:, 0])).long()
     if multi_sweeps:
         cur = pts[:, 3] == 0

