@@ -126,10 +126,10 @@ class _SparseConvFunction(torch.autograd.Function):
         if ctx.needs_input_grad[1]:
             gw = torch.empty((cout, 27, cin), dtype=torch.float32, device=weight.device)
             g_t = gout.t().contiguous()
+            x_pad = torch.cat([features.detach(), features.new_zeros(1, cin)])      # row m_in = "no neighbour" -> zeros
+            idx_all = torch.where(ctx.nbr < 0, x_pad.shape[0] - 1, ctx.nbr).t().contiguous()     # [27, m_out]
             for k in range(27):
-                idx = ctx.nbr[:, k].long()
-                xk = features.detach()[idx.clamp(min=0)] * (idx >= 0).unsqueeze(1).to(features.dtype)
-                gw[:, k, :] = torch.mm(g_t, xk).float()
+                gw[:, k, :] = torch.mm(g_t, x_pad.index_select(0, idx_all[k])).float()
             gw = gw.reshape(weight.shape).to(weight.dtype)
         if ctx.has_bias and ctx.needs_input_grad[2]:
             gb = gout.float().sum(dim=0)
