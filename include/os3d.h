@@ -115,10 +115,20 @@ int os3d_strided_tables(const int32_t *idx, int64_t m, int sz, int sy, int sx, c
  * replaces: SubMConv3d / SparseConv3d / SparseInverseConv3d forward (spconv-cu113; seg3d/utils/spconv_utils.py:16-22). */
 int os3d_spconv_fwd_f32(const float *in, const int32_t *nbr, int64_t m_out, int cin, int cout, const float *w,
                         const float *bias, float *out, void *stream);
+/* Tile order of a kernel map: perm [m] lists the output rows sorted by their set of neighbour offsets (the 27-bit mask,
+ * lexicographic, so similar sets are adjacent) inside blocks of >= 65536 consecutive rows, so that the rows of a 128-row
+ * tile share offsets and the tensor-core kernel skips the others (storage order: ~25 of 27 offsets per tile; sorted: 3.4
+ * for inverse convs, 13.8 for the level-1 submanifold map).  Blocks keep the gather L2-local.  Results do not depend on
+ * the order.  keys, keys_sorted, rows: [m] scratch; temp: os3d_kernel_map_order_scratch(m) bytes (radix sort). */
+int os3d_kernel_map_order_scratch(int64_t m, int64_t *temp_bytes);
+int os3d_kernel_map_order(const int32_t *nbr, int64_t m, uint32_t *keys, uint32_t *keys_sorted, int32_t *rows,
+                          int32_t *perm, void *temp, int64_t temp_bytes, void *stream);
 /* Tile form of a kernel map for the tensor-core path: nbr [m, 27] -> nbr_t [27][m_pad] (offset-major, m_pad = m rounded
- * up to 128, padding rows -1) and tile_mask [m_pad / 128] (bit k set when some row of the 128-row tile has a neighbour
- * at offset k).  Built once per kernel map and shared by every conv that uses the map. */
-int os3d_kernel_map_tiles(const int32_t *nbr, int64_t m, int32_t *nbr_t, uint32_t *tile_mask, void *stream);
+ * up to 128, padding rows -1; row v holds the neighbours of output row perm[v], or of row v when perm is NULL) and
+ * tile_mask [m_pad / 128] (bit k set when some row of the 128-row tile has a neighbour at offset k).  Built once per
+ * kernel map and shared by every conv that uses the map. */
+int os3d_kernel_map_tiles(const int32_t *nbr, int64_t m, const int32_t *perm, int32_t *nbr_t, uint32_t *tile_mask,
+                          void *stream);
 /* bf16 in / bf16 out, f32 accumulate in TMEM on the tcgen05 tensor cores; the gathered operand is fetched by TMA
  * (cp.async.bulk.tensor tile::gather4) straight into the UMMA shared-memory layout.  Fused epilogue:
  * y = acc*scale[c]+shift[c] (bias and folded BatchNorm), optional residual add [m_out, cout] bf16, optional ReLU.
@@ -126,12 +136,13 @@ int os3d_kernel_map_tiles(const int32_t *nbr, int64_t m, int32_t *nbr_t, uint32_
  * channels per row and residual[r, 2c] + residual[r, 2c+1] is added AFTER the ReLU (UpBlock's
  * x_m + channel_reduction(cat), pointtransformer.py:89-110).
  * in: [m_in, cin] bf16 rows, 16-byte aligned, cin % 8 == 0 (callers zero-pad); cout % 16 == 0, cout <= 512
- * (cout % 32 == 0 above 256).  nbr_t / tile_mask: os3d_kernel_map_tiles of the map.  w: os3d_pack_weight_bf16 image.
+ * (cout % 32 == 0 above 256).  nbr_t / tile_mask / perm: os3d_kernel_map_tiles of the map with that perm (NULL =
+ * storage order).  w: os3d_pack_weight_bf16 image.
  * replaces: SubMConv3d / SparseConv3d / SparseInverseConv3d forward (spconv-cu113; seg3d/utils/spconv_utils.py:16-22)
  *           and the BatchNorm1d / ReLU / residual add after them (spconv_utils.py:26-30, pointtransformer.py:47-66). */
-int os3d_spconv_fwd_bf16(const void *in, int64_t m_in, const int32_t *nbr_t, const uint32_t *tile_mask, int64_t m_out,
-                         int cin, int cout, const void *w, const float *scale, const float *shift, const void *residual,
-                         int flags, void *out, void *stream);
+int os3d_spconv_fwd_bf16(const void *in, int64_t m_in, const int32_t *nbr_t, const uint32_t *tile_mask,
+                         const int32_t *perm, int64_t m_out, int cin, int cout, const void *w, const float *scale,
+                         const float *shift, const void *residual, int flags, void *out, void *stream);
 /* spconv 2.x weight [cout, kz, ky, kx, cin] f32 -> kernel layouts.  f32: [27, cin, cout].  bf16: the shared-memory image
  * of the UMMA B operand, [27 * ceil(cin/64)][cout][128 B swizzled] (os3d_spconv_bf16_packed_elems elements). */
 int os3d_spconv_bf16_packed_elems(int cin, int cout, int64_t *elems);

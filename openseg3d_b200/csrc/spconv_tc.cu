@@ -27,6 +27,8 @@
 //
 // replaces: SubMConv3d / SparseConv3d / SparseInverseConv3d forward of spconv-cu113 (+ the BatchNorm1d / ReLU / add
 // that follow them in seg3d/utils/spconv_utils.py:26-30 and seg3d/models/backbones/pointtransformer.py:47-66,89-110).
+#include <cub/device/device_radix_sort.cuh>
+
 #include "common.cuh"
 #include "tc_ptx.cuh"
 
@@ -47,6 +49,7 @@ struct Params {
   int cin;                    // row pitch in elements (multiple of 8)
   const int32_t *nbr_t;       // [27][m_pad] offset-major neighbour rows (-1 = none)
   const uint32_t *tile_mask;  // [m_pad / 128] offsets present in each 128-row tile
+  const int32_t *perm;        // [m_out] output row computed by each row of the (mask-grouped) tile order; NULL = identity
   int64_t m_out, m_pad;
   int n_tiles;
   int cin16;                  // cin rounded up to 16 (MMA K granularity; the excess columns are zero on both operands)
@@ -332,8 +335,9 @@ __global__ void __launch_bounds__(kThreads, 2) spconv_tc_kernel(const Params p) 
       float2 *part = reinterpret_cast<float2 *>(smem);                 // [8 warps][32 lanes]
       for (int t = 0; t < ntile; ++t) {
         const bool has = masks_s[t] != 0u;
-        const int64_t row = (int64_t)(tile0 + t) * kTileM + quarter * 32 + lane;
-        const bool row_ok = row < p.m_out;
+        const int64_t vrow = (int64_t)(tile0 + t) * kTileM + quarter * 32 + lane;
+        const bool row_ok = vrow < p.m_out;
+        const int64_t row = (row_ok && p.perm) ? (int64_t)__ldg(p.perm + vrow) : vrow;
         const __nv_bfloat16 *rrow = (p.residual && row_ok) ? p.residual + row * p.cout : nullptr;
         uint4 na = zero4, nb = zero4;
         if (rrow && half * 16 < p.cout) {
@@ -381,8 +385,9 @@ __global__ void __launch_bounds__(kThreads, 2) spconv_tc_kernel(const Params p) 
     } else {
       for (int t = 0; t < ntile; ++t) {
         const bool has = masks_s[t] != 0u;
-        const int64_t row = (int64_t)(tile0 + t) * kTileM + quarter * 32 + lane;
-        const bool row_ok = row < p.m_out;
+        const int64_t vrow = (int64_t)(tile0 + t) * kTileM + quarter * 32 + lane;
+        const bool row_ok = vrow < p.m_out;
+        const int64_t row = (row_ok && p.perm) ? (int64_t)__ldg(p.perm + vrow) : vrow;
         __nv_bfloat16 *orow = p.out + row * p.ldo;
         const __nv_bfloat16 *rrow = (p.residual && row_ok) ? p.residual + row * p.cout * (pair_sum ? 2 : 1) : nullptr;
         const __nv_bfloat16 *trow = (do_tab && row_ok) ? p.table + (int64_t)__ldg(p.tab_idx + row) * p.tab_cols : nullptr;
@@ -441,21 +446,58 @@ __global__ void __launch_bounds__(kThreads, 2) spconv_tc_kernel(const Params p) 
   }
 }
 
-// [m, 27] row-major kernel map -> offset-major [27][m_pad] (m_pad = 128 * n_tiles, padding rows -1) + per-tile masks.
+// ---- tile order of a kernel map --------------------------------------------------------------------------------
+// An output-stationary tile does the MMAs of every offset that ANY of its 128 rows has, so rows with the same set of
+// neighbour offsets should share tiles.  In storage order a tile of the synthetic Waymo frames has 24.9 (L1 subm) /
+// 26.6 (inverse convs) of the 27 offsets; sorted by mask (lexicographic: similar masks end up adjacent) inside blocks of
+// 65536 consecutive rows it has 13.8 / 3.4 (the inverse conv's rows fall into the 8 parity classes).  Blocks, not a
+// global sort, keep the gather local: a tile's neighbours stay within a window of rows that the concurrent CTAs share
+// in L2.  The sort is one cub radix sort of 32-bit keys (block << 27 | mask) with the row index as value.
+constexpr int kOrderRowsPerCta = 256;
+
+// sort key of every row: (block of consecutive rows) << 27 | 27-bit offset mask; coalesced reads of the row-major map
+__global__ void __launch_bounds__(256) order_keys_kernel(const int32_t *__restrict__ nbr, int64_t m, int block_shift,
+                                                         uint32_t *__restrict__ keys, int32_t *__restrict__ rows) {
+  __shared__ uint32_t bits_s[kOrderRowsPerCta];
+  const int64_t row0 = (int64_t)blockIdx.x * kOrderRowsPerCta;
+  bits_s[threadIdx.x] = 0;
+  __syncthreads();
+  const int n = (int)min((int64_t)kOrderRowsPerCta, m - row0);
+  for (int t = threadIdx.x; t < n * OS3D_KVOL; t += 256) {
+    const int r = t / OS3D_KVOL;
+    if (__ldg(nbr + row0 * OS3D_KVOL + t) >= 0) atomicOr(&bits_s[r], 1u << (t - r * OS3D_KVOL));
+  }
+  __syncthreads();
+  if ((int)threadIdx.x < n) {
+    const int64_t r = row0 + threadIdx.x;
+    keys[r] = ((uint32_t)(r >> block_shift) << OS3D_KVOL) | bits_s[threadIdx.x];
+    rows[r] = (int32_t)r;
+  }
+}
+
+// [m, 27] row-major kernel map -> offset-major [27][m_pad] in tile order (row v of the tile order is output row perm[v];
+// m_pad = 128 * n_tiles, padding rows -1) + per-tile masks.
 __global__ void __launch_bounds__(256) kernel_map_tiles_kernel(const int32_t *__restrict__ nbr, int64_t m, int64_t m_pad,
+                                                               const int32_t *__restrict__ perm,
                                                                int32_t *__restrict__ nbr_t,
                                                                uint32_t *__restrict__ tile_mask) {
   __shared__ int32_t s[kTileM * OS3D_KVOL];
+  __shared__ int32_t rows_s[kTileM];
   __shared__ uint32_t msk;
   const int64_t row0 = (int64_t)blockIdx.x * kTileM;
   if (threadIdx.x == 0) msk = 0;
+  if (threadIdx.x < kTileM) {
+    const int64_t v = row0 + threadIdx.x;
+    rows_s[threadIdx.x] = v < m ? (perm ? __ldg(perm + v) : (int32_t)v) : -1;
+  }
   __syncthreads();
   uint32_t mask = 0;
   for (int t = threadIdx.x; t < kTileM * OS3D_KVOL; t += 256) {
-    const int r = t / OS3D_KVOL;
-    const int32_t v = row0 + r < m ? __ldg(nbr + row0 * OS3D_KVOL + t) : -1;
+    const int r = t / OS3D_KVOL, k = t - r * OS3D_KVOL;
+    const int32_t src = rows_s[r];
+    const int32_t v = src >= 0 ? __ldg(nbr + (int64_t)src * OS3D_KVOL + k) : -1;
     s[t] = v;
-    if (v >= 0) mask |= 1u << (t - r * OS3D_KVOL);
+    if (v >= 0) mask |= 1u << k;
   }
   mask = __reduce_or_sync(0xffffffffu, mask);
   if ((threadIdx.x & 31) == 0 && mask) atomicOr(&msk, mask);
@@ -489,12 +531,41 @@ __global__ void pack_weight_img_kernel(const float *__restrict__ src, int cin, i
 
 using namespace os3d;
 
-extern "C" int os3d_kernel_map_tiles(const int32_t *nbr, int64_t m, int32_t *nbr_t, uint32_t *tile_mask, void *stream) {
+static int order_block_shift(int64_t m) {     // blocks of >= 65536 rows, at most 32 of them (5 key bits above the mask)
+  int shift = 16;
+  while ((m >> shift) >= 32) ++shift;
+  return shift;
+}
+
+extern "C" int os3d_kernel_map_order_scratch(int64_t m, int64_t *temp_bytes) {
+  if (m < 0 || m > 0x7fffffff) return OS3D_ERR_BAD_ARG;
+  size_t bytes = 0;
+  OS3D_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, bytes, (const uint32_t *)nullptr, (uint32_t *)nullptr,
+                                            (const int32_t *)nullptr, (int32_t *)nullptr, (int)m, 0, 32));
+  *temp_bytes = (int64_t)bytes;
+  return 0;
+}
+
+extern "C" int os3d_kernel_map_order(const int32_t *nbr, int64_t m, uint32_t *keys, uint32_t *keys_sorted, int32_t *rows,
+                                     int32_t *perm, void *temp, int64_t temp_bytes, void *stream) {
+  if (m < 0 || m > 0x7fffffff) return OS3D_ERR_BAD_ARG;
+  if (m == 0) return 0;
+  cudaStream_t st = (cudaStream_t)stream;
+  const int shift = order_block_shift(m);
+  tc::order_keys_kernel<<<(unsigned)cdiv(m, tc::kOrderRowsPerCta), 256, 0, st>>>(nbr, m, shift, keys, rows);
+  OS3D_LAUNCH_CHECK();
+  size_t bytes = (size_t)temp_bytes;
+  OS3D_CUDA(cub::DeviceRadixSort::SortPairs(temp, bytes, keys, keys_sorted, rows, perm, (int)m, 0, 32, st));
+  return 0;
+}
+
+extern "C" int os3d_kernel_map_tiles(const int32_t *nbr, int64_t m, const int32_t *perm, int32_t *nbr_t,
+                                     uint32_t *tile_mask, void *stream) {
   if (m < 0) return OS3D_ERR_BAD_ARG;
   if (m == 0) return 0;
   const int64_t n_tiles = cdiv(m, tc::kTileM);
-  tc::kernel_map_tiles_kernel<<<(unsigned)n_tiles, 256, 0, (cudaStream_t)stream>>>(nbr, m, n_tiles * tc::kTileM, nbr_t,
-                                                                                   tile_mask);
+  tc::kernel_map_tiles_kernel<<<(unsigned)n_tiles, 256, 0, (cudaStream_t)stream>>>(nbr, m, n_tiles * tc::kTileM, perm,
+                                                                                   nbr_t, tile_mask);
   OS3D_LAUNCH_CHECK();
   return 0;
 }
@@ -561,7 +632,7 @@ static int launch_tc(tc::Params &p, cudaStream_t stream) {
 }
 
 extern "C" int os3d_spconv_fwd_bf16(const void *in, int64_t m_in, const int32_t *nbr_t, const uint32_t *tile_mask,
-                                    int64_t m_out, int cin, int cout, const void *w, const float *scale,
+                                    const int32_t *perm, int64_t m_out, int cin, int cout, const void *w, const float *scale,
                                     const float *shift, const void *residual, int flags, void *out, void *stream) {
   if (cin <= 0 || cin % 8 || cout < 16 || cout % 16 || cout > 512 || (cout > 256 && cout % 32) ||
       ((scale == nullptr) != (shift == nullptr)) || m_in <= 0 || ((uintptr_t)in & 15))
@@ -572,6 +643,7 @@ extern "C" int os3d_spconv_fwd_bf16(const void *in, int64_t m_in, const int32_t 
   p.cin = cin;
   p.nbr_t = nbr_t;
   p.tile_mask = tile_mask;
+  p.perm = perm;
   p.m_out = m_out;
   p.n_tiles = (int)cdiv(m_out, tc::kTileM);
   p.m_pad = (int64_t)p.n_tiles * tc::kTileM;
@@ -625,6 +697,7 @@ extern "C" int os3d_linear_bf16(const void *x, int64_t m, int k, int n, const vo
   p.cin = k;
   p.nbr_t = nullptr;
   p.tile_mask = nullptr;
+  p.perm = nullptr;
   p.m_out = m;
   p.n_tiles = (int)cdiv(m, tc::kTileM);
   p.m_pad = (int64_t)p.n_tiles * tc::kTileM;

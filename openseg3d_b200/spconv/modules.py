@@ -4,6 +4,7 @@ Parameter names and layouts follow spconv 2.x so reference checkpoints load unch
 [Cout, kz, ky, kx, Cin], optional ``bias`` [Cout].
 """
 import math
+import os
 
 import torch
 import torch.nn as nn
@@ -58,8 +59,8 @@ def sparse_conv_forward(features, nbr, weight, bias, packed_cache, scale=None, s
         out = torch.empty((m_out, cout), dtype=torch.bfloat16, device=features.device)
         if m_out == 0 or features.shape[0] == 0:
             return out.zero_()
-        nbr_t, tile_mask = kernel_map_tiles(nbr)
-        _lib.call('os3d_spconv_fwd_bf16', features, features.shape[0], nbr_t, tile_mask, m_out, cin_pad, cout, w, scale,
+        nbr_t, tile_mask, perm = kernel_map_tiles(nbr)
+        _lib.call('os3d_spconv_fwd_bf16', features, features.shape[0], nbr_t, tile_mask, perm, m_out, cin_pad, cout, w, scale,
                   shift, residual.contiguous() if residual is not None else None, int(relu), out,
                   work=lambda: 2.0 * cin * cout * int((nbr >= 0).sum().item()))
         return out
@@ -67,16 +68,26 @@ def sparse_conv_forward(features, nbr, weight, bias, packed_cache, scale=None, s
 
 
 def kernel_map_tiles(nbr):
-    """(nbr_t [27, m_pad], tile_mask [m_pad / 128]) of a kernel map, built on first use and kept on the map tensor so
-    every conv sharing the map (same ``indice_key``) reuses it."""
+    """(nbr_t [27, m_pad], tile_mask [m_pad / 128], perm [m]) of a kernel map -- its tile form in mask-grouped row order
+    (os3d_kernel_map_order) -- built on first use and kept on the map tensor so every conv sharing the map (same
+    ``indice_key``) reuses it."""
     hit = getattr(nbr, '_os3d_tiles', None)
     if hit is None:
         m = nbr.shape[0]
         n_tiles = (m + 127) // 128
         nbr_t = torch.empty((27, n_tiles * 128), dtype=torch.int32, device=nbr.device)
         tile_mask = torch.empty(n_tiles, dtype=torch.int32, device=nbr.device)
-        _lib.call('os3d_kernel_map_tiles', nbr, m, nbr_t, tile_mask)
-        hit = nbr._os3d_tiles = (nbr_t, tile_mask)
+        perm = None
+        if os.environ.get('OS3D_MAP_ORDER', '1') != '0':
+            import ctypes
+            scratch = torch.empty((3, m), dtype=torch.int32, device=nbr.device)      # keys, sorted keys, row ids
+            perm = torch.empty(m, dtype=torch.int32, device=nbr.device)
+            nbytes = ctypes.c_int64(0)
+            _lib.lib().os3d_kernel_map_order_scratch(m, ctypes.byref(nbytes))
+            temp = torch.empty(max(nbytes.value, 1), dtype=torch.uint8, device=nbr.device)
+            _lib.call('os3d_kernel_map_order', nbr, m, scratch[0], scratch[1], scratch[2], perm, temp, nbytes.value)
+        _lib.call('os3d_kernel_map_tiles', nbr, m, perm, nbr_t, tile_mask)
+        hit = nbr._os3d_tiles = (nbr_t, tile_mask, perm)
     return hit
 
 
