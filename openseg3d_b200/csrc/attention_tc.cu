@@ -151,6 +151,7 @@ __global__ void __launch_bounds__(kThreads, KB == 32 ? 8 : (DP <= 32 ? 4 : 3)) w
   const uint32_t tmem_row = tmem_base + ((uint32_t)(warp * 32) << 16);
   const uint32_t idesc1 = make_idesc_bf16(kTileQ, kBlockKeys), idesc2 = make_idesc_bf16(kTileQ, DP);
   const float scale = 1.4426950408889634f / fmaxf(__ldg(p.tau), p.tau_min);
+  const bool fixed_max = scale <= 60.0f;
 
   float m_run = -INFINITY, l_run = 0.0f;
   uint32_t ph1 = 0, ph2 = 0;
@@ -273,16 +274,32 @@ __global__ void __launch_bounds__(kThreads, KB == 32 ? 8 : (DP <= 32 ? 4 : 3)) w
         for (int i = 0; i < 32; ++i) s[32 + i] = __uint_as_float(r[i]);
       }
     }
-    float m_new = m_run;                                           // maxima are kept in raw (unscaled) score units
+    // q and k are unit vectors, so a raw score never exceeds 1 (+ bf16 rounding): with a moderate temperature the
+    // softmax can use the FIXED reference maximum 1 -- no running maximum, no FMNMX per score, no rescaling of O --
+    // and cannot underflow (2 * scale <= 120 binades).  Small temperatures keep the online maximum.
+    const uint64_t full_mask = kBlockKeys == 64 ? ~0ull : ((1ull << (kBlockKeys & 63)) - 1ull);
+    const bool all_valid = __all_sync(0xffffffffu, valid == full_mask);
+    float m_new = m_run, neg_ms;
+    if (fixed_max) {
+      if (!all_valid) {
 #pragma unroll
-    for (int j = 0; j < kBlockKeys; ++j) {
-      const bool ok = ((j < 32 ? v_lo : v_hi) >> (j & 31)) & 1u;
-      s[j] = ok ? s[j] : -INFINITY;
-      m_new = fmaxf(m_new, s[j]);
+        for (int j = 0; j < kBlockKeys; ++j) {
+          const bool ok = ((j < 32 ? v_lo : v_hi) >> (j & 31)) & 1u;
+          s[j] = ok ? s[j] : -INFINITY;
+        }
+      }
+      neg_ms = -scale;
+    } else {
+#pragma unroll
+      for (int j = 0; j < kBlockKeys; ++j) {                       // maxima are kept in raw (unscaled) score units
+        const bool ok = ((j < 32 ? v_lo : v_hi) >> (j & 31)) & 1u;
+        s[j] = ok ? s[j] : -INFINITY;
+        m_new = fmaxf(m_new, s[j]);
+      }
+      const float m_use = (m_new == -INFINITY) ? 0.0f : m_new;    // nothing valid so far: ex2(-inf) = 0 everywhere
+      alpha = ex2_ftz((m_run - m_use) * scale);        // m_run = -inf -> 0 (l_run, O are still 0 then)
+      neg_ms = -m_use * scale;
     }
-    const float m_use = (m_new == -INFINITY) ? 0.0f : m_new;      // nothing valid so far: ex2(-inf) = 0 everywhere
-    alpha = ex2_ftz((m_run - m_use) * scale);          // m_run = -inf -> 0 (l_run, O are still 0 then)
-    const float neg_ms = -m_use * scale;
     float l_blk = 0.0f;
 #pragma unroll
     for (int j = 0; j < kBlockKeys; j += 2) {
@@ -383,7 +400,7 @@ extern "C" int os3d_window_attention_bf16_tc(const void *q, const void *k, const
   dim3 grid((unsigned)(cdiv(m, attn_tc::kTileQ) * heads));
   cudaStream_t st = (cudaStream_t)stream;
   const char *e = getenv("OS3D_ATTN_KB");                       // tuning override: keys per block for dp = 16
-  const bool kb32 = e ? atoi(e) == 32 : true;
+  const bool kb32 = e ? atoi(e) != 64 : true;
   if (dp == 16 && kb32) attn_tc::window_attention_tc_kernel<16, 32><<<grid, attn_tc::kThreads, 0, st>>>(p);
   else if (dp == 16) attn_tc::window_attention_tc_kernel<16, 64><<<grid, attn_tc::kThreads, 0, st>>>(p);
   else if (dp == 32) attn_tc::window_attention_tc_kernel<32, 64><<<grid, attn_tc::kThreads, 0, st>>>(p);

@@ -118,10 +118,11 @@ def test_partition_empty_and_single():
     assert out.shape == (1, 48) and bool(torch.isfinite(out).all())
 
 
-@pytest.mark.parametrize('c', [48, 96, 192, 384])
-def test_attention_tensor_core_bf16_vs_fp32_path(c):
-    """tcgen05 attention (bf16, head-padded, in-kernel normalisation, online softmax with TMEM rescale) against the
-    fp32 SIMT path that the reference golden pins; windows from 1 to several hundred tokens (multi key-block tiles)."""
+@pytest.mark.parametrize('c,tau', [(48, 0.2), (96, 0.2), (192, 0.2), (384, 0.2), (96, 0.02), (192, 0.005)])
+def test_attention_tensor_core_bf16_vs_fp32_path(c, tau):
+    """tcgen05 attention (bf16, head-padded, in-kernel normalisation) against the fp32 SIMT path that the reference
+    golden pins; windows from 1 to several hundred tokens (multi key-block tiles).  tau 0.2: fixed-maximum softmax
+    (unit vectors bound the scores); tau 0.02 / 0.005 (clamped to tau_min 0.01): online maximum with TMEM rescale."""
     from openseg3d_b200 import spconv
     from openseg3d_b200.models import SparseWindowPartitionLayer, WindowAttention
     rng = np.random.default_rng(c)
@@ -141,7 +142,7 @@ def test_attention_tensor_core_bf16_vs_fp32_path(c):
     layer = SparseWindowPartitionLayer(binfo, (10, 10, 8), (200, 200, 16))
     attn = WindowAttention(c, 8, 0.0).cuda().eval()
     with torch.no_grad():
-        attn.self_attn.tau.fill_(0.2)
+        attn.self_attn.tau.fill_(tau)
         for prm in attn.parameters():                              # bf16-representable weights: isolate kernel error
             prm.copy_(prm.bfloat16().float())
         info32 = layer(spconv.SparseConvTensor(feats.float(), coords, [16, 200, 200], 2))
@@ -153,4 +154,5 @@ def test_attention_tensor_core_bf16_vs_fp32_path(c):
             assert int(seg.seg_len[:int(seg.level_info[13])].max()) > (400 if s == 0 else 200)   # many key blocks
             err = (out.float() - ref).abs().max().item() / ref.abs().max().item()
             mean_err = (out.float() - ref).abs().mean().item() / ref.abs().mean().item()
-            assert err < 3e-2 and mean_err < 1e-2, (s, err, mean_err)
+            # sharp softmax (small tau) amplifies the bf16 rounding of the scores
+            assert err < (3e-2 if tau >= 0.1 else 8e-2) and mean_err < (1e-2 if tau >= 0.1 else 2e-2), (s, err, mean_err)
