@@ -60,7 +60,7 @@ __global__ void __launch_bounds__(kThreads, KB == 32 ? 8 : (DP <= 32 ? 4 : 3)) w
   constexpr int kChunks = DP / 8;                         // 16-byte chunks per head slice
   constexpr int kSboQ = kChunks * kLbo + 16;              // +16: stagger 8-row groups across banks
   constexpr int kSboP = (kBlockKeys / 8) * kLbo + 16;
-  constexpr int kSboV = (kBlockKeys / 8) * kLbo + 16;     // V^T: rows = head dims, K = keys
+  constexpr int kSboV = (kBlockKeys / 8) * kLbo + 16;     // V as the MN-major B operand: stride between 8-dim groups; 8-key groups are kLbo apart
   constexpr int kQBytes = (kTileQ / 8) * kSboQ;
   constexpr int kKBytes = (kBlockKeys / 8) * kSboQ;
   constexpr int kVBytes = (DP / 8) * kSboV;
@@ -149,7 +149,7 @@ __global__ void __launch_bounds__(kThreads, KB == 32 ? 8 : (DP <= 32 ? 4 : 3)) w
   tc_fence_after();
   const uint32_t tmem_base = tmem_slot;
   const uint32_t tmem_row = tmem_base + ((uint32_t)(warp * 32) << 16);
-  const uint32_t idesc1 = make_idesc_bf16(kTileQ, kBlockKeys), idesc2 = make_idesc_bf16(kTileQ, DP);
+  const uint32_t idesc1 = make_idesc_bf16(kTileQ, kBlockKeys), idesc2 = make_idesc_bf16(kTileQ, DP) | (1u << 16);   // bit 16: B is MN-major
   const float scale = 1.4426950408889634f / fmaxf(__ldg(p.tau), p.tau_min);
   const bool fixed_max = scale <= 60.0f;
 
@@ -214,19 +214,17 @@ __global__ void __launch_bounds__(kThreads, KB == 32 ? 8 : (DP <= 32 ? 4 : 3)) w
         }
         *reinterpret_cast<uint4 *>(k_s + core_off(key, c, kSboQ)) = make_uint4(w[0], w[1], w[2], w[3]);
       }
-      // V^T: element (dim n, key) -> (n/8)*sbo + (key/8)*lbo + (n%8)*16 + (key%8)*2
+      // V is the B operand of O += P V with N = head dims, K = keys.  Its rows (keys) are stored as they come from
+      // global memory -- 16-byte chunks of 8 dims -- in the MN-major no-swizzle core-matrix layout:
+      //   element (dim n, key) -> (n / 8) * sbo + (key / 8) * lbo + (key % 8) * 16 + (n % 8) * 2
+      // so the gather is plain vector stores (the K-major layout needed V transposed: 2-byte scattered stores, 65 % of
+      // the LSU data-pipe wavefronts of the kernel).
 #pragma unroll
       for (int cv = 0; cv < kVChunks; ++cv) {
         const int c = 2 * cv + half;
         if (c >= kChunks) continue;
         const uint4 u = k_ok_next ? v_raw[cv] : make_uint4(0, 0, 0, 0);
-        const uint32_t w[4] = {u.x, u.y, u.z, u.w};
-        uint8_t *dst = v_s + c * kSboV + (key >> 3) * kLbo + (key & 7) * 2;
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          *reinterpret_cast<uint16_t *>(dst + (2 * i) * 16) = (uint16_t)(w[i] & 0xffffu);
-          *reinterpret_cast<uint16_t *>(dst + (2 * i + 1) * 16) = (uint16_t)(w[i] >> 16);
-        }
+        *reinterpret_cast<uint4 *>(v_s + c * kSboV + (key >> 3) * kLbo + (key & 7) * 16) = u;
       }
     }
     fence_proxy_async();
