@@ -237,6 +237,16 @@ def main():
                 'per_entry_ms': {e: round(by[e][0], 3) for e in entries if e in by},
                 'other_kernels_ms_per_step': {k: round(v[0], 3) for k, v in sorted(by.items()) if k not in entries}}
 
+    # HBM-bound kernels of stages 1-2 (+ the position-table gather-add): achieved = algorithmic bytes / CUDA-event time
+    hbm_names = ['os3d_voxelize', 'os3d_scatter_max_f32', 'os3d_scatter_mean_f32', 'os3d_gather_rows', 'os3d_subm_table',
+                 'os3d_strided_tables', 'os3d_kernel_map_tiles', 'os3d_add_table_rows']
+    roofline['hbm_kernels'] = {
+        k: {'ms': round(by[k][0], 3), 'algorithmic_mb': round(by[k][1] / 1e6, 1),
+            'achieved_gbs': round(by[k][1] / (by[k][0] * 1e-3) / 1e9, 1) if by[k][0] else 0.0,
+            'frac_of_hbm_peak': round(by[k][1] / (by[k][0] * 1e-3) / 1e9 / pk['hbm'], 3) if by[k][0] else 0.0}
+        for k in hbm_names if k in by and by[k][1] > 0}
+    roofline['hbm_peak_gbs'] = pk['hbm']
+
     line = {'metric': 'points/sec, Waymo 1-sweep seg forward', 'value': value, 'unit': 'points/s', 'n_gpus': world,
             'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': total_ms / args.steps, 'higher_is_better': True,
             'scaling': 'weak', 'vs_baseline': None, 'dtype': args.dtype, 'data': 'synthetic',

@@ -41,7 +41,8 @@ def voxelize_batch(points, voxel_size, point_cloud_range, has_batch=True):
     num = torch.zeros(1, dtype=torch.int32, device=dev)
     _lib.call('os3d_voxelize', points, n, stride, int(has_batch), float(pcr[0]), float(pcr[1]), float(pcr[2]),
               float(vs[0]), float(vs[1]), float(vs[2]), int(grid[0]), int(grid[1]), int(grid[2]), table, cap.value,
-              slot_of, block_sums, nb.value, coors, pvid, num)
+              slot_of, block_sums, nb.value, coors, pvid, num,
+              work=lambda: n * (stride * 4 + 8 + 16))        # points in, ids out, <= one coordinate row per point
     m = int(num.item())
     return coors[:m], pvid
 

@@ -25,31 +25,37 @@ __global__ void hash_build_kernel(const int4 *__restrict__ idx, int64_t m, int s
   table[s].val = (int32_t)i;  // sites are unique, so exactly one writer per slot
 }
 
-// One thread per (row, k); writes are perfectly coalesced, the 4-int coordinate load is a broadcast inside the
-// 27 consecutive threads of a row.
+// The submanifold map is symmetric: nbr[i, k] = j  <=>  nbr[j, 26 - k] = i.  One thread per (row, k <= 13) probes the
+// site table (half the random L2 accesses of probing all 27 offsets -- the probes are what this kernel costs) and
+// writes both entries; the table is pre-filled with -1.  The 4-int coordinate load is a broadcast inside the 14
+// consecutive threads of a row.
+constexpr int kSubmHalf = 14;       // offsets 0..13 (13 = centre)
 __global__ void subm_table_kernel(const int4 *__restrict__ idx, int64_t m, int sz, int sy, int sx,
                                   const os3d_slot_t *__restrict__ table, uint64_t mask, int32_t *__restrict__ nbr,
                                   int32_t *__restrict__ pair_count) {
   const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   int found = 0;
-  if (t < m * OS3D_KVOL) {
-    const int64_t i = t / OS3D_KVOL;
-    const int k = (int)(t - i * OS3D_KVOL);
+  if (t < m * kSubmHalf) {
+    const int64_t i = t / kSubmHalf;
+    const int k = (int)(t - i * kSubmHalf);
     const int4 c = __ldg(idx + i);
-    int32_t j;
     if (k == 13) {
-      j = (int32_t)i;  // centre offset is the identity map
+      nbr[i * OS3D_KVOL + 13] = (int32_t)i;  // centre offset is the identity map
+      found = 1;
     } else {
       const int z = c.y + k / 9 - 1, y = c.z + (k / 3) % 3 - 1, x = c.w + k % 3 - 1;
-      j = (z >= 0 && z < sz && y >= 0 && y < sy && x >= 0 && x < sx)
-              ? table_find(table, mask, lin4(c.x, z, y, x, sz, sy, sx)) : -1;
+      const int32_t j = (z >= 0 && z < sz && y >= 0 && y < sy && x >= 0 && x < sx)
+                            ? table_find(table, mask, lin4(c.x, z, y, x, sz, sy, sx)) : -1;
+      if (j >= 0) {
+        nbr[i * OS3D_KVOL + k] = j;
+        nbr[(int64_t)j * OS3D_KVOL + (26 - k)] = (int32_t)i;
+        found = 2;
+      }
     }
-    nbr[t] = j;
-    found = j >= 0;
   }
-  // warp-aggregated pair count (diagnostic)
-  const unsigned ballot = __ballot_sync(0xffffffffu, found);
-  if ((threadIdx.x & 31) == 0 && ballot) atomicAdd(pair_count, __popc(ballot));
+  // pair count (diagnostic): one atomic per CTA
+  const int both = __syncthreads_count(found == 2), one = __syncthreads_count(found == 1);
+  if (threadIdx.x == 0 && (both | one)) atomicAdd(pair_count, 2 * both + one);
 }
 
 // ---- strided conv: output sites --------------------------------------------------------------------
@@ -134,33 +140,18 @@ __global__ void __launch_bounds__(kScanThreads) bitmap_expand_kernel(const uint3
   if (blockIdx.x == 0 && threadIdx.x == 0) *num_out = block_sums[n_blocks];
 }
 
-// fwd_nbr: one thread per (output row, k): input site i = 2o - 1 + k.
-__global__ void strided_fwd_kernel(const int4 *__restrict__ out_idx, int64_t m_out, int sz, int sy, int sx,
-                                   const os3d_slot_t *__restrict__ table, uint64_t mask, int32_t *__restrict__ fwd_nbr,
-                                   int32_t *__restrict__ pair_count) {
+// Both tables of a strided conv from the input side, one thread per (input row i, k): the output site is
+// o = (i + 1 - k) / 2 when integral and in range, its row the rank of its bit in the bitmap (an O(1), cache-local
+// lookup -- no hash probes).  The pair (k: i -> o) is written to inv_nbr[i, k] (coalesced) and to fwd_nbr[o, k]
+// (scattered; fwd_nbr is pre-filled with -1).  Probing the input hash table from the output side, as the first
+// version did, cost 27 random L2 accesses per output row.
+__global__ void strided_pairs_kernel(const int4 *__restrict__ idx, int64_t m, int oz, int oy, int ox,
+                                     const uint32_t *__restrict__ bitmap, const int32_t *__restrict__ word_prefix,
+                                     int32_t *__restrict__ inv_nbr, int32_t *__restrict__ fwd_nbr,
+                                     int32_t *__restrict__ pair_count) {
   const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   int found = 0;
-  if (t < m_out * OS3D_KVOL) {
-    const int64_t r = t / OS3D_KVOL;
-    const int k = (int)(t - r * OS3D_KVOL);
-    const int4 o = __ldg(out_idx + r);
-    const int z = 2 * o.y - 1 + k / 9, y = 2 * o.z - 1 + (k / 3) % 3, x = 2 * o.w - 1 + k % 3;
-    const int32_t j = (z >= 0 && z < sz && y >= 0 && y < sy && x >= 0 && x < sx)
-                          ? table_find(table, mask, lin4(o.x, z, y, x, sz, sy, sx)) : -1;
-    fwd_nbr[t] = j;
-    found = j >= 0;
-  }
-  const unsigned ballot = __ballot_sync(0xffffffffu, found);
-  if ((threadIdx.x & 31) == 0 && ballot) atomicAdd(pair_count, __popc(ballot));
-}
-
-// inv_nbr: one thread per (input row, k): output site o = (i + 1 - k) / 2 when integral and in range; its row is the
-// rank of its bit in the bitmap.
-__global__ void strided_inv_kernel(const int4 *__restrict__ idx, int64_t m, int oz, int oy, int ox,
-                                   const uint32_t *__restrict__ bitmap, const int32_t *__restrict__ word_prefix,
-                                   int32_t *__restrict__ inv_nbr) {
-  const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (t >= m * OS3D_KVOL) return;
+  if (t < m * OS3D_KVOL) {
   const int64_t i = t / OS3D_KVOL;
   const int k = (int)(t - i * OS3D_KVOL);
   const int4 c = __ldg(idx + i);
@@ -176,6 +167,14 @@ __global__ void strided_inv_kernel(const int4 *__restrict__ idx, int64_t m, int 
     }
   }
   inv_nbr[t] = r;
+  if (r >= 0) {
+    fwd_nbr[(int64_t)r * OS3D_KVOL + k] = (int32_t)i;
+    found = 1;
+  }
+  }
+  // one atomic per CTA: a same-address atomic per warp (a million of them) costs more than the lookups
+  const int cta_pairs = __syncthreads_count(found);
+  if (threadIdx.x == 0 && cta_pairs) atomicAdd(pair_count, cta_pairs);
 }
 
 }  // namespace os3d
@@ -197,9 +196,11 @@ extern "C" int os3d_subm_table(const int32_t *idx, int64_t m, int sz, int sy, in
                                int64_t cap, int32_t *nbr, int32_t *pair_count, void *stream) {
   cudaStream_t st = (cudaStream_t)stream;
   OS3D_CUDA(cudaMemsetAsync(pair_count, 0, sizeof(int32_t), st));
-  if (m > 0)
-    subm_table_kernel<<<(unsigned)cdiv(m * OS3D_KVOL, 256), 256, 0, st>>>((const int4 *)idx, m, sz, sy, sx, table,
+  if (m > 0) {
+    OS3D_CUDA(cudaMemsetAsync(nbr, 0xff, (size_t)m * OS3D_KVOL * sizeof(int32_t), st));      // -1 = no neighbour
+    subm_table_kernel<<<(unsigned)cdiv(m * kSubmHalf, 256), 256, 0, st>>>((const int4 *)idx, m, sz, sy, sx, table,
                                                                          (uint64_t)cap - 1, nbr, pair_count);
+  }
   OS3D_LAUNCH_CHECK();
   return 0;
 }
@@ -227,13 +228,10 @@ extern "C" int os3d_strided_tables(const int32_t *idx, int64_t m, int sz, int sy
                                    int32_t *inv_nbr, int32_t *pair_count, void *stream) {
   cudaStream_t st = (cudaStream_t)stream;
   OS3D_CUDA(cudaMemsetAsync(pair_count, 0, sizeof(int32_t), st));
-  if (m_out > 0)
-    strided_fwd_kernel<<<(unsigned)cdiv(m_out * OS3D_KVOL, 256), 256, 0, st>>>((const int4 *)out_idx, m_out, sz, sy, sx,
-                                                                              table, (uint64_t)cap - 1, fwd_nbr,
-                                                                              pair_count);
+  if (m_out > 0) OS3D_CUDA(cudaMemsetAsync(fwd_nbr, 0xff, (size_t)m_out * OS3D_KVOL * sizeof(int32_t), st));
   if (m > 0)
-    strided_inv_kernel<<<(unsigned)cdiv(m * OS3D_KVOL, 256), 256, 0, st>>>((const int4 *)idx, m, oz, oy, ox, bitmap,
-                                                                          word_prefix, inv_nbr);
+    strided_pairs_kernel<<<(unsigned)cdiv(m * OS3D_KVOL, 256), 256, 0, st>>>((const int4 *)idx, m, oz, oy, ox, bitmap,
+                                                                            word_prefix, inv_nbr, fwd_nbr, pair_count);
   OS3D_LAUNCH_CHECK();
   return 0;
 }

@@ -119,7 +119,7 @@ class PosDict(dict):
             return x + self['flat'].to(x.dtype)
         out = torch.empty_like(x)
         _lib.call('os3d_add_table_rows', x, self.table_as(x.dtype), self.pos_idx, x.shape[0], x.shape[1], x.element_size(),
-                  out)
+                  out, work=lambda: 2 * x.numel() * x.element_size() + x.shape[0] * 4)
         return out
 
     @property

@@ -22,7 +22,8 @@ class _ScatterMax(Function):
     def forward(ctx, feats, ids, m, fix_empty):
         f, i = _prep(feats, ids)
         out = torch.empty((m, f.shape[1]), dtype=torch.float32, device=f.device)
-        _lib.call('os3d_scatter_max_f32', f, i, f.shape[0], f.shape[1], out, m, int(fix_empty))
+        _lib.call('os3d_scatter_max_f32', f, i, f.shape[0], f.shape[1], out, m, int(fix_empty),
+                  work=lambda: (f.shape[0] + m) * f.shape[1] * 4 + f.shape[0] * 8)
         ctx.save_for_backward(f, i, out)
         ctx.in_dtype = feats.dtype
         return out
@@ -41,7 +42,8 @@ class _ScatterMean(Function):
         f, i = _prep(feats, ids)
         out = torch.empty((m, f.shape[1]), dtype=torch.float32, device=f.device)
         counts = torch.empty(m, dtype=torch.int32, device=f.device)
-        _lib.call('os3d_scatter_mean_f32', f, i, f.shape[0], f.shape[1], out, counts, None, m)
+        _lib.call('os3d_scatter_mean_f32', f, i, f.shape[0], f.shape[1], out, counts, None, m,
+                  work=lambda: (f.shape[0] + m) * f.shape[1] * 4 + f.shape[0] * 8)
         ctx.save_for_backward(i, counts)
         ctx.n, ctx.in_dtype = f.shape[0], feats.dtype
         return out

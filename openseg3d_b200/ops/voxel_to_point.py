@@ -14,7 +14,8 @@ class _Gather(Function):
         feats = feats.contiguous()
         ids = coords.long().contiguous()
         out = torch.empty((ids.shape[0], feats.shape[-1]), dtype=feats.dtype, device=feats.device)
-        _lib.call('os3d_gather_rows', feats, ids, ids.shape[0], feats.shape[-1], feats.element_size(), out)
+        _lib.call('os3d_gather_rows', feats, ids, ids.shape[0], feats.shape[-1], feats.element_size(), out,
+                  work=lambda: (ids.shape[0] + feats.shape[0]) * feats.shape[-1] * feats.element_size() + ids.shape[0] * 8)
         ctx.save_for_backward(ids)
         ctx.m = feats.shape[0]
         return out

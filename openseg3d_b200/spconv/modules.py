@@ -86,7 +86,7 @@ def kernel_map_tiles(nbr):
             _lib.lib().os3d_kernel_map_order_scratch(m, ctypes.byref(nbytes))
             temp = torch.empty(max(nbytes.value, 1), dtype=torch.uint8, device=nbr.device)
             _lib.call('os3d_kernel_map_order', nbr, m, scratch[0], scratch[1], scratch[2], perm, temp, nbytes.value)
-        _lib.call('os3d_kernel_map_tiles', nbr, m, perm, nbr_t, tile_mask)
+        _lib.call('os3d_kernel_map_tiles', nbr, m, perm, nbr_t, tile_mask, work=lambda: 2 * m * 27 * 4 + m * 4)
         hit = nbr._os3d_tiles = (nbr_t, tile_mask, perm)
     return hit
 

@@ -64,7 +64,7 @@ def build_subm_rulebook(x):
     nbr = torch.empty((m, 27), dtype=torch.int32, device=x.indices.device)
     pairs = torch.zeros(1, dtype=torch.int32, device=x.indices.device)
     z, y, xx = x.spatial_shape
-    _lib.call('os3d_subm_table', x.indices, m, z, y, xx, table, cap, nbr, pairs)
+    _lib.call('os3d_subm_table', x.indices, m, z, y, xx, table, cap, nbr, pairs, work=lambda: m * (16 + 27 * 4))
     return SubmRulebook(nbr, pairs, x.indices, list(x.spatial_shape))
 
 
@@ -93,5 +93,5 @@ def build_strided_rulebook(x):
     inv = torch.empty((m, 27), dtype=torch.int32, device=dev)
     pairs = torch.zeros(1, dtype=torch.int32, device=dev)
     _lib.call('os3d_strided_tables', x.indices, m, sz, sy, sx, table, cap, out_idx, m_out, oz, oy, ox, bitmap, prefix, fwd,
-              inv, pairs)
+              inv, pairs, work=lambda: (m + m_out) * (16 + 27 * 4))
     return StridedRulebook(x.indices, [sz, sy, sx], out_idx, [oz, oy, ox], fwd, inv, pairs)

@@ -220,3 +220,41 @@ def test_spconv_bf16_strided_and_inverse_modules():
     e2 = (z.features.float().cpu() - ref_z).abs().max().item() / ref_z.abs().max().item()
     assert e1 < 2e-2 and e2 < 2e-2, (e1, e2)
     assert z.indices is x.indices
+
+
+def test_full_size_conv_is_independent_of_tile_order(monkeypatch):
+    """BASELINE size (8 synthetic frames, ~0.93 M voxels at level 1 / ~1.0 M at level 2): the mask-sorted tile order
+    (os3d_kernel_map_order) only changes WHICH tile computes a row, never the arithmetic of the row, so the bf16
+    tensor-core conv must give bit-identical outputs in storage order and in sorted order; perm must be a permutation."""
+    from openseg3d_b200 import spconv, synthetic
+    from openseg3d_b200.core import voxelize_batch
+    from openseg3d_b200.spconv.modules import sparse_conv_forward, kernel_map_tiles, _PackedWeights
+    frames = 8
+    pts, _ = synthetic.make_batch(list(range(frames)), 1, False)
+    coors, _ = voxelize_batch(torch.from_numpy(pts).cuda(), [0.1, 0.1, 0.1], [-72, -72, -2, 72, 72, 4.4])
+    x = spconv.SparseConvTensor(torch.zeros(coors.shape[0], 1, device='cuda'), coors, [64, 1440, 1440], frames)
+    rb = spconv.build_strided_rulebook(x)
+    torch.manual_seed(0)
+    for nbr, m_in, cin, cout in ((spconv.build_subm_rulebook(x).nbr, coors.shape[0], 48, 48),
+                                 (rb.fwd_nbr, coors.shape[0], 48, 96), (rb.inv_nbr, rb.out_indices.shape[0], 96, 48)):
+        feats = torch.randn(m_in, cin, device='cuda').bfloat16()
+        w = torch.randn(cout, 3, 3, 3, cin, device='cuda') * 0.05
+        outs = []
+        for order in ('0', '1'):
+            monkeypatch.setenv('OS3D_MAP_ORDER', order)
+            if hasattr(nbr, '_os3d_tiles'):
+                del nbr._os3d_tiles
+            outs.append(sparse_conv_forward(feats, nbr, w, None, _PackedWeights(), None, None, None, True))
+            _, tile_mask, perm = kernel_map_tiles(nbr)
+            if order == '1':
+                assert bool((torch.sort(perm.long()).values == torch.arange(nbr.shape[0], device='cuda')).all())
+                sorted_offsets = tile_mask
+            else:
+                assert perm is None
+                storage_offsets = tile_mask
+        assert torch.equal(outs[0], outs[1])
+
+        def offsets_per_tile(t):
+            t = t.long() & 0x7ffffff
+            return sum(((t >> b) & 1) for b in range(27)).float().mean().item()
+        assert offsets_per_tile(sorted_offsets) < offsets_per_tile(storage_offsets)
