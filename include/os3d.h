@@ -259,6 +259,16 @@ int os3d_window_attention_bf16_tc(const void *q, const void *k, const void *v, i
 int os3d_layernorm_residual(const void *x, const void *resid, const float *w, const float *b, int64_t m, int c,
                             float eps, int elem_size, void *out, void *stream);
 
+/* ---------------------------------------------------------------- loss side --- */
+
+/* k nearest points (squared distances, ascending) of every query among the points of its own batch segment.
+ * xyz [n, 3], new_xyz [m, 3] f32; offset / new_offset [n_seg] int32: cumulative segment ends of xyz / new_xyz;
+ * idx [m, nsample] int32, dist2 [m, nsample] f32 (squared); 1 <= nsample <= 100.  Exact brute force with the
+ * reference's heap semantics (ties keep the lower index).
+ * replaces: knn_query_ext.knn_query_cuda (seg3d/ops/knn_query/src/knn_query_cuda.cu:67-133; tools/train.py:103). */
+int os3d_knn_query(const float *xyz, const float *new_xyz, int64_t m, int nsample, const int32_t *offset,
+                   const int32_t *new_offset, int n_seg, int32_t *idx, float *dist2, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -56,6 +56,7 @@ SIGNATURES = {
                              PTR, PTR],
     'os3d_window_attention_bf16_tc': [PTR, PTR, PTR, I64, I64, I64, I32, I32, PTR, PTR, PTR, PTR, F32, PTR, I64, PTR],
     'os3d_pos_embed': [PTR, I64, I32, I32, I32, I32, F32, I32, PTR, PTR],
+    'os3d_knn_query': [PTR, PTR, I64, I32, PTR, PTR, I32, PTR, PTR, PTR],
     'os3d_add_table_rows': [PTR, PTR, PTR, I64, I32, I32, PTR, PTR],
     'os3d_layernorm_residual': [PTR, PTR, PTR, PTR, I64, I32, F32, I32, PTR, PTR],
     'os3d_qk_normalize': [PTR, PTR, I64, I64, I32, I32, I32, PTR],

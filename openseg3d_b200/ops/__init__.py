@@ -1,7 +1,8 @@
-"""Operator namespace mirroring seg3d/ops/__init__.py:1-6 (knn_query is out of the hot path)."""
+"""Operator namespace mirroring seg3d/ops/__init__.py:1-6."""
 from .pooling import voxel_avg_pooling, voxel_max_pooling, scatter_max, scatter_mean
 from .voxel_to_point import voxel_to_point
+from .knn_query import knn_query
 from .ingroup_inds import get_inner_win_inds
 
-__all__ = ['voxel_avg_pooling', 'voxel_max_pooling', 'voxel_to_point', 'get_inner_win_inds', 'scatter_max',
+__all__ = ['voxel_avg_pooling', 'voxel_max_pooling', 'voxel_to_point', 'knn_query', 'get_inner_win_inds', 'scatter_max',
            'scatter_mean']

@@ -184,6 +184,51 @@ def sparse_conv_c(features, nbr, weight, bias=None):
     return out
 
 
+def knn_query(nsample, xyz, new_xyz, offset, new_offset):
+    """knn_query_cuda_kernel (seg3d/ops/knn_query/src/knn_query_cuda.cu:67-112) restated serially: per query a max-heap
+    of the nsample best squared distances (root = worst; replaced only when strictly closer), keys of the query's batch
+    segment in ascending order, heap-sorted ascending at the end.  float32 arithmetic, one rounding per operation.
+    Returns (idx int32 [m, nsample], dist2 float32 [m, nsample]) -- squared distances, as the kernel writes them.
+    parity unpinned: the reference kernel is GPU-only and cannot run in the build container."""
+    xyz = np.ascontiguousarray(xyz, np.float32)
+    new_xyz = np.ascontiguousarray(new_xyz, np.float32)
+    offset, new_offset = np.asarray(offset, np.int64), np.asarray(new_offset, np.int64)
+    m = new_xyz.shape[0]
+    idx = np.zeros((m, nsample), np.int32)
+    d2o = np.zeros((m, nsample), np.float32)
+
+    def sift(dist, ind, k):                        # reheap, knn_query_cuda.cu:23-38
+        root, child = 0, 1
+        while child < k:
+            if child + 1 < k and dist[child + 1] > dist[child]:
+                child += 1
+            if dist[root] > dist[child]:
+                return
+            dist[root], dist[child] = dist[child], dist[root]
+            ind[root], ind[child] = ind[child], ind[root]
+            root, child = child, 2 * child + 1
+
+    for q in range(m):
+        b = 0
+        while q >= new_offset[b]:
+            b += 1
+        start, end = (0 if b == 0 else int(offset[b - 1])), int(offset[b])
+        d = new_xyz[q][None, :] - xyz[start:end]                                   # float32
+        d2 = (d[:, 0] * d[:, 0] + d[:, 1] * d[:, 1]) + d[:, 2] * d[:, 2]           # float32, no FMA
+        dist = [np.float32(1e10)] * nsample
+        ind = [start] * nsample
+        for i in range(end - start):
+            if d2[i] < dist[0]:
+                dist[0], ind[0] = d2[i], start + i
+                sift(dist, ind, nsample)
+        for i in range(nsample - 1, 0, -1):        # heap_sort, :41-49
+            dist[0], dist[i] = dist[i], dist[0]
+            ind[0], ind[i] = ind[i], ind[0]
+            sift(dist, ind, i)
+        idx[q], d2o[q] = ind, dist
+    return idx, d2o
+
+
 # ------------------------------------------------------------------------------------------------
 # Stage 4 -- window partition (swformer_utils.py, point_transformer_layer.py)
 # ------------------------------------------------------------------------------------------------
