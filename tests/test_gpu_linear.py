@@ -63,3 +63,19 @@ def test_linear_bf16_rejects_bad_input():
     with pytest.raises(RuntimeError):
         linear_bf16(torch.randn(10, 64).bfloat16(), chunks)              # CPU tensor
     assert linear_bf16(torch.zeros(0, 64, dtype=torch.bfloat16).cuda(), chunks).shape == (0, 48)
+
+
+def test_gelu_bf16_matches_erf_gelu():
+    """os3d_gelu_bf16 (fast erf, |error| <= 1.5e-7) against torch's exact erf GELU in float64, rounded to bf16: equal
+    up to one bf16 ulp at round-to-nearest ties."""
+    from openseg3d_b200 import _lib
+    x = torch.cat([torch.linspace(-12, 12, 80000), torch.randn(19992) * 3, torch.tensor([0.0, -0.0, 1e-8, -1e-8, 30.0, -30.0, 5.5, -5.5])])
+    x = x.bfloat16().cuda()
+    out = torch.empty_like(x)
+    _lib.call('os3d_gelu_bf16', x, x.numel(), out)
+    ref = F.gelu(x.double()).cpu()
+    got = out.double().cpu()
+    ulp = ref.abs() * 2.0 ** -7 + 1e-12          # one bf16 ulp; results below 1e-12 in magnitude are all 'zero'
+    assert bool(((got - ref).abs() <= ulp).all()), float(((got - ref).abs() / ulp).max())
+    exact = (out.cpu() == ref.bfloat16()).float().mean().item()
+    assert exact > 0.995, exact
