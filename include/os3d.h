@@ -210,6 +210,11 @@ int os3d_group_partition(const int64_t *group, int64_t n, int64_t n_groups, cons
  * replaces: SparseWindowPartitionLayer.get_pos_embed (point_transformer_layer.py:152-207). */
 int os3d_pos_embed(const int32_t *in_win, int64_t m, int c, int win_x, int win_y, int win_z, float temperature,
                    int elem_size, void *out, void *stream);
+/* out[r, :] = x[r, :] * (bias + table[idx[r], :]): per-point application of the per-frame squeeze-excite gate
+ * (table f32 [frames, c], idx int64 [m] = batch index; bias 1 folds the segmentor's residual x + x * gate).
+ * replaces: `x * y[indices]` of FlattenSELayer.forward (se_layer.py:29-30) and the add in segformer.py:134. */
+int os3d_scale_rows_by_table(const void *x, const float *table, const int64_t *idx, int64_t m, int c, float bias,
+                             int elem_size, void *out, void *stream);
 /* out = GELU(x) (erf form) on n bf16 elements (n % 8 == 0; out may alias x).  erf by Abramowitz-Stegun 7.1.26,
  * |error| <= 1.5e-7: at most one bf16 ulp from the exact erf GELU (98.7 % of results bit-identical after rounding).
  * replaces: MLP.act = nn.GELU() between fc1 and fc2 (point_transformer_layer.py:260-276). */

@@ -59,6 +59,7 @@ SIGNATURES = {
     'os3d_knn_query': [PTR, PTR, I64, I32, PTR, PTR, I32, PTR, PTR, PTR],
     'os3d_add_table_rows': [PTR, PTR, PTR, I64, I32, I32, PTR, PTR],
     'os3d_gelu_bf16': [PTR, I64, PTR, PTR],
+    'os3d_scale_rows_by_table': [PTR, PTR, PTR, I64, I32, F32, I32, PTR, PTR],
     'os3d_layernorm_residual': [PTR, PTR, PTR, PTR, I64, I32, F32, I32, PTR, PTR],
     'os3d_qk_normalize': [PTR, PTR, I64, I64, I32, I32, I32, PTR],
     'os3d_window_attention': [PTR, PTR, PTR, I64, I64, I64, I32, I32, PTR, PTR, PTR, PTR, ctypes.POINTER(ctypes.c_int * 4), PTR,

@@ -168,6 +168,42 @@ extern "C" int os3d_gelu_bf16(const void *x, int64_t n, void *out, void *stream)
   return 0;
 }
 
+// out[r, :] = x[r, :] * (bias + table[idx[r], :])   -- the squeeze-excite gate of FlattenSELayer applied per point:
+// x * gate[batch_idx] (bias 0) or, with the residual the segmentor adds, x + x * gate[batch_idx] (bias 1)
+// (se_layer.py:24-30, segformer.py:134).  idx: int64 batch index per row; the table has one row per frame.
+template <typename T>
+__global__ void __launch_bounds__(256) scale_rows_by_table_kernel(const T *__restrict__ x, const float *__restrict__ table,
+                                                                   const int64_t *__restrict__ idx, int64_t m, int chunks,
+                                                                   float bias, T *__restrict__ out) {
+  const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= m * chunks) return;
+  const int64_t r = t / chunks;
+  const int c = (int)(t - r * chunks) * 8;
+  const int64_t c_total = (int64_t)chunks * 8;
+  float a[8], g[8];
+  Vec8<T>::load(x + r * c_total + c, a);
+  Vec8<float>::load(table + __ldg(idx + r) * c_total + c, g);
+#pragma unroll
+  for (int i = 0; i < 8; ++i) a[i] *= bias + g[i];
+  Vec8<T>::store(out + r * c_total + c, a);
+}
+
+extern "C" int os3d_scale_rows_by_table(const void *x, const float *table, const int64_t *idx, int64_t m, int c, float bias,
+                                        int elem_size, void *out, void *stream) {
+  if (c <= 0 || c % 8 || (elem_size != 2 && elem_size != 4)) return OS3D_ERR_BAD_ARG;
+  if (m == 0) return 0;
+  const int chunks = c / 8;
+  const unsigned g = (unsigned)cdiv(m * chunks, 256);
+  if (elem_size == 2)
+    scale_rows_by_table_kernel<__nv_bfloat16><<<g, 256, 0, (cudaStream_t)stream>>>(
+        (const __nv_bfloat16 *)x, table, idx, m, chunks, bias, (__nv_bfloat16 *)out);
+  else
+    scale_rows_by_table_kernel<float><<<g, 256, 0, (cudaStream_t)stream>>>((const float *)x, table, idx, m, chunks, bias,
+                                                                            (float *)out);
+  OS3D_LAUNCH_CHECK();
+  return 0;
+}
+
 extern "C" int os3d_add_table_rows(const void *x, const void *table, const int32_t *idx, int64_t m, int c, int elem_size,
                                    void *out, void *stream) {
   if (c <= 0 || c % 8 || (elem_size != 2 && elem_size != 4)) return OS3D_ERR_BAD_ARG;

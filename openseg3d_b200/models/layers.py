@@ -539,6 +539,21 @@ class FlattenSELayer(nn.Module):
         self.fc = nn.Sequential(nn.Linear(channel, channel // reduction, bias=False), nn.ReLU(inplace=True),
                                 nn.Linear(channel // reduction, channel, bias=False), nn.Sigmoid())
 
+    def gate(self, x, indices, batch_size=None):
+        """Per-frame channel gate [B, C] (fp32): sigmoid(fc(mean over the frame's points))."""
+        return self.fc(scatter_mean(x, indices.long(), batch_size).float())
+
+    def residual_forward(self, x, indices, batch_size=None):
+        """x + forward(x) in one pass over the points (inference): x * (1 + gate[batch index])."""
+        if torch.is_grad_enabled() or x.shape[1] % 8 or x.dtype not in (torch.float32, torch.bfloat16):
+            return x + self.forward(x, indices, batch_size)
+        indices = indices.long().contiguous()
+        x = x.contiguous()
+        out = torch.empty_like(x)
+        _lib.call('os3d_scale_rows_by_table', x, self.gate(x, indices, batch_size).contiguous(), indices, x.shape[0],
+                  x.shape[1], 1.0, x.element_size(), out, work=lambda: 2 * x.numel() * x.element_size() + x.shape[0] * 8)
+        return out
+
     def forward(self, x, indices, batch_size=None):
         indices = indices.long()
         pooled = scatter_mean(x, indices, batch_size)

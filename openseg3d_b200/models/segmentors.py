@@ -184,7 +184,7 @@ class Segformer(nn.Module):
             fused = torch.cat([point_per_features.to(point_voxel_features.dtype), point_voxel_features], dim=1)
             fused = self._folded('fusion_encoder')(fused, self.compute_dtype) if fold else self.fusion_encoder(fused)
             batch_idx = raw[:, 0][cur_point_indices] if self.use_multi_sweeps else raw[:, 0]
-            fused = fused + self.se(fused, batch_idx, batch_dict['batch_size'])
+            fused = self.se.residual_forward(fused, batch_idx, batch_dict['batch_size'])     # fused + se(fused)
             point_out = self._folded('classifier')(fused, self.compute_dtype) if fold else self.classifier(fused)
 
         result = OrderedDict()
