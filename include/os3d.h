@@ -164,6 +164,15 @@ int os3d_linear_bf16(const void *x, int64_t m, int k, int n, const void *w, cons
                      const void *residual, const float *ln_gamma, const float *ln_beta, float ln_eps, const void *table,
                      const int32_t *tab_idx, int tab_cols, void *out, int64_t ldo, void *stream);
 
+/* The same operation on the persistent Linear kernel (linear_tc.cu): weights resident in shared memory, activations by
+ * TMA tile loads, double-buffered accumulators so the epilogue of one row tile overlaps the loads and MMAs of the next.
+ * Same arguments as os3d_linear_bf16; needs n <= 256 and the weight image to fit next to the activation ring
+ * (os3d_linear_tc_fits(k, n) != 0) -- callers fall back to os3d_linear_bf16 otherwise. */
+int os3d_linear_tc_fits(int k, int n);
+int os3d_linear_tc_bf16(const void *x, int64_t m, int k, int n, const void *w, const float *bias, int flags,
+                        const void *residual, const float *ln_gamma, const float *ln_beta, float ln_eps, const void *table,
+                        const int32_t *tab_idx, int tab_cols, void *out, int64_t ldo, void *stream);
+
 /* ---------------------------------------------------------------- stage 4: window partition + attention --- */
 
 #define OS3D_MAX_LEVELS 4

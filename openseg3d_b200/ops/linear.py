@@ -2,12 +2,14 @@
 residual + LayerNorm, and the position-embedding table term of the q / k projection.  bf16 activations only; there is
 no fallback -- other dtypes raise."""
 import ctypes
+import os
 
 import torch
 
 from .. import _lib
 
 RELU, GELU, LAYERNORM, TABLE = 1, 4, 8, 16
+_USE_TC = os.environ.get('OS3D_LINEAR_TC', '1') != '0'
 
 
 class PackedLinearCache(object):
@@ -71,8 +73,9 @@ def linear_bf16(x, chunks, flags=0, residual=None, ln=None, table=None, tab_idx=
     for i, (packed, bias, off, width) in enumerate(chunks):
         tab = table[i] if table is not None else None
         dst = out if off == 0 and width == n else out[:, off:]
-        _lib.lib()          # make sure the library is loaded before taking raw pointers
-        _lib.call('os3d_linear_bf16', x, m, k, width, packed, bias, flags,
+        # persistent kernel (weights resident, overlapped epilogue) when the weights fit; else the conv kernel's dense mode
+        entry = 'os3d_linear_tc_bf16' if _lib.lib().os3d_linear_tc_fits(k, width) and _USE_TC else 'os3d_linear_bf16'
+        _lib.call(entry, x, m, k, width, packed, bias, flags,
                   residual.contiguous() if residual is not None else None, gamma, beta, float(eps), tab, tab_idx,
                   tab.shape[1] if tab is not None else 0, _Ptr(dst), n,
                   work=lambda w=width: 2.0 * m * k * w)
