@@ -253,9 +253,9 @@ __global__ void __launch_bounds__(kThreads, 1) linear_tc_kernel(const __grid_con
 #pragma unroll
             for (int i = 0; i < 16; ++i) y[i] = fmaxf(y[i], 0.0f);
           }
-          if (do_gelu) {               // exact (erf) GELU, nn.GELU() default (point_transformer_layer.py:266)
+          if (do_gelu) {               // erf-form GELU, nn.GELU() default (point_transformer_layer.py:266)
 #pragma unroll
-            for (int i = 0; i < 16; ++i) y[i] = 0.5f * y[i] * (1.0f + erff(y[i] * 0.70710678118654752f));
+            for (int i = 0; i < 16; ++i) y[i] = gelu_erf_fast(y[i]);
           }
           store16(p.out + row * p.ldo + col, y);
         }

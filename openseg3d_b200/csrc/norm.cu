@@ -136,18 +136,6 @@ __global__ void __launch_bounds__(256) add_table_rows_kernel(const T *__restrict
 // makes torch's kernel compute-bound on B200 (3.3 TB/s); here erf comes from Abramowitz-Stegun 7.1.26
 // (|error| <= 1.5e-7: at most one bf16 ulp in the result, 98.7 % bit-identical): erf(z) = 1 - (a1 t + ... + a5 t^5) exp(-z^2),
 // t = 1 / (1 + p z), z >= 0 -- one reciprocal, one ex2, six FMAs.
-__device__ __forceinline__ float gelu_erf_fast(float x) {
-  const float z = fabsf(x) * 0.70710678118654752f;
-  const float t = __fdividef(1.0f, fmaf(0.3275911f, z, 1.0f));
-  float poly = fmaf(1.061405429f, t, -1.453152027f);
-  poly = fmaf(poly, t, 1.421413741f);
-  poly = fmaf(poly, t, -0.284496736f);
-  poly = fmaf(poly, t, 0.254829592f);
-  const float e = poly * t * exp2f(-1.4426950408889634f * z * z);     // 1 - erf(z)
-  const float half_erfc = 0.5f * e;                                   // Phi(-|x|)
-  return x >= 0.0f ? x * (1.0f - half_erfc) : x * half_erfc;          // x * Phi(x)
-}
-
 __global__ void __launch_bounds__(256) gelu_bf16_kernel(const __nv_bfloat16 *__restrict__ x, int64_t n8,
                                                         __nv_bfloat16 *__restrict__ out) {
   const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;

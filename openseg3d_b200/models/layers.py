@@ -498,6 +498,8 @@ class EncoderLayer(nn.Module):
             heads, o_c = mha.attention_heads(x, pos_dict, ind_dict['segments'])
             cache = self.__dict__.setdefault('_lin', PackedLinearCache())
             x1 = linear_bf16(heads, o_c, residual=x, ln=_ln_params(self.norm1))
+            # fc1 stays a library GEMM + the in-place GELU kernel: os3d_linear_bf16's GELU epilogue measured the same
+            # (L3: 0.29 ms vs 0.12 + 0.16 ms) -- the fused epilogue pays off where it removes a pass (LayerNorm)
             h = linear_in(self.mlp.fc1, x1)
             _lib.call('os3d_gelu_bf16', h, h.numel(), h, work=lambda: 2 * h.numel() * 2)          # in place
             return linear_bf16(h, cache.get('fc2', self.mlp.fc2.weight, self.mlp.fc2.bias, max_width=512), residual=x1,
