@@ -208,10 +208,11 @@ def main():
     _lib.PROFILE = None
     by = {}
     for name, e0, e1, work in prof:
-        d = by.setdefault(name, [0.0, 0.0, 0])
+        d = by.setdefault(name, [0.0, 0.0, 0, 0.0])
         d[0] += e0.elapsed_time(e1)
         d[1] += work
         d[2] += 1
+        d[3] += getattr(work, 'bytes', 0.0)
     pk = peaks()
     # The dominant kernel is spconv_tc_kernel: the sparse convolutions (os3d_spconv_fwd_bf16) and, in its dense mode, the
     # LayerNorm-fused Linear layers of the SWFormer blocks (os3d_linear_bf16).  achieved = algorithmic FLOPs of all its
@@ -223,9 +224,9 @@ def main():
     else:
         entries = ['os3d_spconv_fwd_f32']
         kname = 'spconv_f32_kernel'
-    conv_ms = sum(by.get(e, [0.0, 0.0, 0])[0] for e in entries)
-    conv_flops = sum(by.get(e, [0.0, 0.0, 0])[1] for e in entries)
-    conv_n = sum(by.get(e, [0.0, 0.0, 0])[2] for e in entries)
+    conv_ms = sum(by.get(e, [0.0, 0.0, 0, 0.0])[0] for e in entries)
+    conv_flops = sum(by.get(e, [0.0, 0.0, 0, 0.0])[1] for e in entries)
+    conv_n = sum(by.get(e, [0.0, 0.0, 0, 0.0])[2] for e in entries)
     achieved = conv_flops / (conv_ms * 1e-3) / 1e12 if conv_ms else 0.0
     traffic, traffic_src = None, None
     prof_dir = os.path.join(ROOT, 'profiles')
@@ -250,6 +251,14 @@ def main():
             'frac_of_hbm_peak': round(by[k][1] / (by[k][0] * 1e-3) / 1e9 / pk['hbm'], 3) if by[k][0] else 0.0}
         for k in hbm_names if k in by and by[k][1] > 0}
     roofline['hbm_peak_gbs'] = pk['hbm']
+    # the persistent Linear kernel (linear_tc_kernel: out-proj/fc2 + residual + LayerNorm, table-mode q|k projection): its
+    # tensor work is small next to its activations, so HBM bounds it -- bytes = x + out (+ residual) + weights (+ row ids)
+    lt = by.get('os3d_linear_tc_bf16')
+    if lt and lt[0]:
+        roofline['linear_tc_kernel'] = {
+            'ms': round(lt[0], 3), 'launches_per_step': lt[2], 'algorithmic_mb': round(lt[3] / 1e6, 1),
+            'achieved_gbs': round(lt[3] / (lt[0] * 1e-3) / 1e9, 1), 'frac_of_hbm_peak': round(lt[3] / (lt[0] * 1e-3) / 1e9 / pk['hbm'], 3),
+            'achieved_tflops': round(lt[1] / (lt[0] * 1e-3) / 1e12, 1)}
 
     line = {'metric': 'points/sec, Waymo 1-sweep seg forward', 'value': value, 'unit': 'points/s', 'n_gpus': world,
             'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': total_ms / args.steps, 'higher_is_better': True,

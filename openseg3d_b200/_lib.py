@@ -120,6 +120,15 @@ _launches = 0
 PROFILE = None      # bench.py sets this to a list to collect (name, start_event, end_event, work) per call
 
 
+class Work(float):
+    """Algorithmic FLOPs of a call that also carries its algorithmic HBM bytes (``.bytes``) for the bench's roofline table."""
+
+    def __new__(cls, flops, nbytes=0.0):
+        w = super().__new__(cls, flops)
+        w.bytes = float(nbytes)
+        return w
+
+
 def launches():
     """Number of libos3d CUDA kernels launched so far (bench.py reports the delta over its timed region)."""
     return _launches

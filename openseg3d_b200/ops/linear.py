@@ -78,7 +78,9 @@ def linear_bf16(x, chunks, flags=0, residual=None, ln=None, table=None, tab_idx=
         _lib.call(entry, x, m, k, width, packed, bias, flags,
                   residual.contiguous() if residual is not None else None, gamma, beta, float(eps), tab, tab_idx,
                   tab.shape[1] if tab is not None else 0, _Ptr(dst), n,
-                  work=lambda w=width: 2.0 * m * k * w)
+                  work=lambda w=width: _lib.Work(2.0 * m * k * w,
+                                                 2.0 * (m * k + m * w * (2 if residual is not None else 1) + k * w)
+                                                 + (4.0 * m if tab is not None else 0.0)))
     return out
 
 
