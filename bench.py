@@ -244,13 +244,22 @@ def main():
 
     # HBM-bound kernels of stages 1-2 (+ the position-table gather-add): achieved = algorithmic bytes / CUDA-event time
     hbm_names = ['os3d_voxelize', 'os3d_scatter_max_f32', 'os3d_scatter_mean_f32', 'os3d_gather_rows', 'os3d_subm_table',
-                 'os3d_strided_tables', 'os3d_kernel_map_tiles', 'os3d_add_table_rows']
+                 'os3d_strided_tables', 'os3d_kernel_map_tiles', 'os3d_window_partition', 'os3d_add_table_rows',
+                 'os3d_gelu_bf16']
     roofline['hbm_kernels'] = {
         k: {'ms': round(by[k][0], 3), 'algorithmic_mb': round(by[k][1] / 1e6, 1),
             'achieved_gbs': round(by[k][1] / (by[k][0] * 1e-3) / 1e9, 1) if by[k][0] else 0.0,
             'frac_of_hbm_peak': round(by[k][1] / (by[k][0] * 1e-3) / 1e9 / pk['hbm'], 3) if by[k][0] else 0.0}
         for k in hbm_names if k in by and by[k][1] > 0}
     roofline['hbm_peak_gbs'] = pk['hbm']
+    # window attention: useful FLOPs = 4 * sum_windows n^2 * C (QK^T + PV over real tokens only; the reference pads to max_tokens)
+    at = by.get('os3d_window_attention_bf16_tc')
+    if at and at[0] and at[1]:
+        roofline['window_attention_tc_kernel'] = {
+            'ms': round(at[0], 3), 'launches_per_step': at[2], 'useful_gflop': round(at[1] / 1e9, 1),
+            'achieved_tflops': round(at[1] / (at[0] * 1e-3) / 1e12, 1),
+            'frac_of_tensor_peak': round(at[1] / (at[0] * 1e-3) / 1e12 / pk['tensor'], 4),
+            'note': 'instruction bound in the softmax (ncu: profiles/r01c_attention_l2_full.txt), not by the tensor pipe'}
     # the persistent Linear kernel (linear_tc_kernel: out-proj/fc2 + residual + LayerNorm, table-mode q|k projection): its
     # tensor work is small next to its activations, so HBM bounds it -- bytes = x + out (+ residual) + weights (+ row ids)
     lt = by.get('os3d_linear_tc_bf16')

@@ -173,6 +173,29 @@ int os3d_linear_tc_bf16(const void *x, int64_t m, int k, int n, const void *w, c
                         const void *residual, const float *ln_gamma, const float *ln_beta, float ln_eps, const void *table,
                         const int32_t *tab_idx, int tab_cols, void *out, int64_t ldo, void *stream);
 
+/* A chain of 2..4 Linear layers in one persistent kernel (mlp_tc.cu), activations kept in shared / tensor memory:
+ *   y = L_{n-1}(... act_0(L_0(a0))),  L_l(a) = a . W_l^T + b_l,  act: 0 none, 1 ReLU, 2 exact (erf) GELU.
+ * a0 is either the bf16 matrix x [m, layers[0].k] (pitch ldx elements; x32 = NULL) or the output of an fp32 front layer
+ * computed in the kernel from x32 [m, k32 <= 16] (pitch ld32 floats): a0 = act32(x32 . w32 + b32), w32 [k32][64] fp32,
+ * 64 wide (x = NULL).  The last layer may add `residual` [m, n] (pitch ldr) after an optional LayerNorm (gamma / beta
+ * non-NULL): out = residual + LN(L(a)), as in EncoderLayer.  out: bf16 (or fp32 when out_f32) [m, n_out] with pitch ldo
+ * elements; n_out <= layers[last].n drops zero-padded output columns.
+ * layers[l].w is an os3d_pack_linear_bf16 image of the [n, k] weight; widths are multiples of 16 up to 256 and
+ * layers[l].k == layers[l-1].n.  os3d_mlp_chain_fits() != 0 when all weight images fit in shared memory.
+ * replaces: point_encoder / fusion_encoder / classifier of Segformer with eval-mode BatchNorm folded
+ *           (seg3d/models/segmentors/segformer.py:21-32,58-76,105-116) and the MLP + norm2 of EncoderLayer
+ *           (seg3d/models/layers/point_transformer_layer.py:260-298). */
+typedef struct {
+  const void *w;       /* packed bf16 weight image */
+  const float *bias;   /* [n] or NULL */
+  int k, n, act;
+} os3d_mlp_layer;
+int os3d_mlp_chain_fits(const os3d_mlp_layer *layers, int n_layers, int has_front);
+int os3d_mlp_chain_bf16(const void *x, int64_t m, int64_t ldx, const float *x32, int64_t ld32, int k32, const float *w32,
+                        const float *b32, int act32, const os3d_mlp_layer *layers, int n_layers, const void *residual,
+                        int64_t ldr, const float *ln_gamma, const float *ln_beta, float ln_eps, void *out, int64_t ldo,
+                        int n_out, int out_f32, void *stream);
+
 /* ---------------------------------------------------------------- stage 4: window partition + attention --- */
 
 #define OS3D_MAX_LEVELS 4

@@ -23,6 +23,12 @@ class WindowCfg(ctypes.Structure):
                [('lvl_lo', ctypes.c_int * 4), ('lvl_hi', ctypes.c_int * 4), ('lvl_tokens', ctypes.c_int * 4)]
 
 
+class MlpLayer(ctypes.Structure):
+    """os3d_mlp_layer (include/os3d.h)."""
+    _fields_ = [('w', ctypes.c_void_p), ('bias', ctypes.c_void_p), ('k', ctypes.c_int), ('n', ctypes.c_int),
+                ('act', ctypes.c_int)]
+
+
 # name -> argtypes (the trailing stream argument included); every function returns int
 SIGNATURES = {
     'os3d_voxelize_scratch': [I64, ctypes.POINTER(I64), ctypes.POINTER(I64)],
@@ -51,6 +57,9 @@ SIGNATURES = {
     'os3d_linear_bf16': [PTR, I64, I32, I32, PTR, PTR, I32, PTR, PTR, PTR, F32, PTR, PTR, I32, PTR, I64, PTR],
     'os3d_linear_tc_bf16': [PTR, I64, I32, I32, PTR, PTR, I32, PTR, PTR, PTR, F32, PTR, PTR, I32, PTR, I64, PTR],
     'os3d_linear_tc_fits': [I32, I32],
+    'os3d_mlp_chain_fits': [ctypes.POINTER(MlpLayer), I32, I32],
+    'os3d_mlp_chain_bf16': [PTR, I64, I64, PTR, I64, I32, PTR, PTR, I32, ctypes.POINTER(MlpLayer), I32, PTR, I64, PTR, PTR, F32,
+                            PTR, I64, I32, I32, PTR],
     'os3d_pack_weight_bf16': [PTR, I32, I32, PTR, PTR],
     'os3d_window_partition': [PTR, I64, I32, ctypes.POINTER(WindowCfg), PTR, PTR, PTR, I64, PTR, PTR, PTR, PTR, PTR, PTR,
                               PTR, PTR, PTR, PTR, PTR],
@@ -112,7 +121,7 @@ KERNELS_PER_CALL = {
     'os3d_voxelize': 5, 'os3d_cart2polar_rows': 1, 'os3d_scatter_max_f32': 2, 'os3d_scatter_mean_f32': 2,
     'os3d_scatter_max_bwd_f32': 1, 'os3d_scatter_mean_bwd_f32': 1, 'os3d_gather_rows': 1, 'os3d_scatter_add_rows_f32': 1,
     'os3d_hash_build': 1, 'os3d_subm_table': 1, 'os3d_strided_sites': 4, 'os3d_strided_tables': 2,
-    'os3d_spconv_fwd_f32': 1, 'os3d_spconv_fwd_bf16': 1, 'os3d_pack_weight_f32': 1, 'os3d_pack_weight_bf16': 1, 'os3d_kernel_map_tiles': 1, 'os3d_kernel_map_order': 2, 'os3d_linear_bf16': 1, 'os3d_linear_tc_bf16': 1, 'os3d_pack_linear_bf16': 1,
+    'os3d_spconv_fwd_f32': 1, 'os3d_spconv_fwd_bf16': 1, 'os3d_pack_weight_f32': 1, 'os3d_pack_weight_bf16': 1, 'os3d_kernel_map_tiles': 1, 'os3d_kernel_map_order': 2, 'os3d_linear_bf16': 1, 'os3d_linear_tc_bf16': 1, 'os3d_pack_linear_bf16': 1, 'os3d_mlp_chain_bf16': 1,
     'os3d_window_partition': 7, 'os3d_group_partition': 7, 'os3d_pos_embed': 1, 'os3d_qk_normalize': 1,
     'os3d_window_attention': 1, 'os3d_window_attention_bwd': 2, 'os3d_window_attention_bf16_tc': 1, 'os3d_layernorm_residual': 1,
 }
@@ -127,6 +136,13 @@ class Work(float):
         w = super().__new__(cls, flops)
         w.bytes = float(nbytes)
         return w
+
+
+class _Raw(object):
+    """A raw device address as a call() argument (a strided view's base pointer; the pitch travels separately)."""
+
+    def __init__(self, ptr):
+        self.ptr = ptr
 
 
 def launches():
@@ -147,7 +163,8 @@ def call(name, *args, work=None):
     rc = getattr(L, name)(*conv, stream())
     if prof is not None:
         e1.record()
-        prof.append((name, e0, e1, float(work()) if work is not None else 0.0))
+        w = work() if work is not None else 0.0
+        prof.append((name, e0, e1, w if isinstance(w, float) else float(w)))
     _launches += KERNELS_PER_CALL.get(name, 1)
     if rc != 0:
         raise RuntimeError(f'{name} failed: {L.os3d_error_string(rc).decode()} (code {rc})')

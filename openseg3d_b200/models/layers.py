@@ -9,6 +9,7 @@ The padded per-level view the reference exposes (flat2win inds, padded pos-embed
 through ``materialize()`` for callers and tests that want it.
 """
 import ctypes
+import os
 
 import numpy as np
 import torch
@@ -19,6 +20,9 @@ from .. import _lib
 from .._lib import WindowCfg
 from ..ops.pooling import scatter_mean
 from ..ops.linear import PackedLinearCache, linear_bf16
+from ..ops.mlp_chain import GELU as MLP_GELU, NONE as MLP_NONE, MlpChain
+
+_USE_MLP_CHAIN = os.environ.get('OS3D_MLP_CHAIN', '1') != '0'
 
 
 class WindowSegments(object):
@@ -27,6 +31,13 @@ class WindowSegments(object):
     def __init__(self, cfg, batching_info, m):
         self.cfg, self.batching_info, self.m = cfg, batching_info, m
         self.lvl_tokens = (ctypes.c_int * 4)(*[cfg.lvl_tokens[i] for i in range(4)])
+
+    def sum_sq_tokens(self):
+        """sum over windows of n^2 (bench accounting only: useful attention FLOPs = 4 * sum n^2 * C); one host read, cached."""
+        if not hasattr(self, '_sum_sq'):
+            n = torch.unique(self.win_id, return_counts=True)[1].double()
+            self._sum_sq = float((n * n).sum().item())
+        return self._sum_sq
 
     def check_no_drop(self):
         """One host read: raises if any token would be dropped (the reference cannot continue either, App. C)."""
@@ -203,7 +214,8 @@ class SparseWindowPartitionLayer(nn.Module):
         block_sums = torch.empty((nb + 1) * 5, **i32)
         _lib.call('os3d_window_partition', indices, m, batch_size, ctypes.byref(cfg), win_count, win_meta, block_sums, nb,
                   seg.win_id, seg.in_win, seg.level, seg.win_rank, seg.inner, seg.order, seg.seg_start, seg.seg_len,
-                  seg.pos_seg, seg.level_info)
+                  seg.pos_seg, seg.level_info,
+                  work=lambda: m * (16 + 4 * 12) + 8 * n_win)       # coords in; ids / ranks / order / segments out; histogram
         return seg
 
     @torch.no_grad()
@@ -345,7 +357,7 @@ class CosineMultiheadAttention(nn.MultiheadAttention):
         out = torch.empty((m, hd), dtype=feat.dtype, device=feat.device)
         _lib.call('os3d_window_attention_bf16_tc', qk, qk.data_ptr() + hd * 2, v, 2 * hd, hd, m, self.num_heads, dp,
                   seg.order, seg.pos_seg, seg.level_info, self.tau.detach().float().reshape(1), float(self.tau_min),
-                  out, hd)
+                  out, hd, work=lambda: 4.0 * seg.sum_sq_tokens() * self.embed_dim)
         return out, o_c
 
     def tensor_core_ok(self, feat):
@@ -498,8 +510,12 @@ class EncoderLayer(nn.Module):
             heads, o_c = mha.attention_heads(x, pos_dict, ind_dict['segments'])
             cache = self.__dict__.setdefault('_lin', PackedLinearCache())
             x1 = linear_bf16(heads, o_c, residual=x, ln=_ln_params(self.norm1))
-            # fc1 stays a library GEMM + the in-place GELU kernel: os3d_linear_bf16's GELU epilogue measured the same
-            # (L3: 0.29 ms vs 0.12 + 0.16 ms) -- the fused epilogue pays off where it removes a pass (LayerNorm)
+            chain = self._mlp_chain()
+            if chain is not None:
+                # fc1 -> GELU -> fc2 -> LayerNorm + residual in one kernel: the [M, 2C] hidden tensor stays on chip
+                return chain(x1, residual=x1, ln=_ln_params(self.norm2))
+            # wider layers (weights beyond shared memory): fc1 is a library GEMM + the in-place GELU kernel --
+            # os3d_linear_bf16's GELU epilogue measured the same (L3: 0.29 ms vs 0.12 + 0.16 ms)
             h = linear_in(self.mlp.fc1, x1)
             _lib.call('os3d_gelu_bf16', h, h.numel(), h, work=lambda: 2 * h.numel() * 2)          # in place
             return linear_bf16(h, cache.get('fc2', self.mlp.fc2.weight, self.mlp.fc2.bias, max_width=512), residual=x1,
@@ -510,6 +526,22 @@ class EncoderLayer(nn.Module):
             return x + self.drop_path(layer_norm_in(self.norm2, self.mlp(x)))
         x = residual_layer_norm(self.norm1, attn, x)
         return residual_layer_norm(self.norm2, self.mlp(x), x)
+
+
+    def _mlp_chain(self):
+        """MlpChain of fc1 / GELU / fc2 when both weight matrices fit in shared memory (C <= 96), else None.  Rebuilt when
+        a parameter changes."""
+        if not _USE_MLP_CHAIN:
+            return None
+        fc1, fc2 = self.mlp.fc1, self.mlp.fc2
+        tag = tuple((t.data_ptr(), t._version) for t in (fc1.weight, fc1.bias, fc2.weight, fc2.bias))
+        hit = self.__dict__.get('_chain')
+        if hit is None or hit[0] != tag:
+            chain = None
+            if MlpChain.fits([tuple(fc1.weight.shape), tuple(fc2.weight.shape)]):
+                chain = MlpChain([(fc1.weight, fc1.bias, MLP_GELU), (fc2.weight, fc2.bias, MLP_NONE)])
+            hit = self.__dict__['_chain'] = (tag, chain)
+        return hit[1]
 
 
 class SWFormerBlock(nn.Module):

@@ -7,6 +7,7 @@ Two additions for the B200 path, both optional so that reference-shaped batch di
   * ``compute_dtype=torch.bfloat16`` runs the backbone in bf16 (tcgen05 sparse conv, bf16 attention) and the point
     MLPs under bf16 autocast; voxelization and pooling always stay fp32.
 """
+import os
 from collections import OrderedDict
 from types import SimpleNamespace
 
@@ -16,9 +17,13 @@ import torch.nn as nn
 
 from ..core.voxel import voxelize_batch, _geometry
 from ..ops import voxel_to_point
+from ..ops.mlp_chain import NONE, RELU, MlpChain
 from .backbones import PointTransformer
 from .layers import FlattenSELayer
 from .voxel_encoders import VFE
+
+
+_USE_MLP_CHAIN = os.environ.get('OS3D_MLP_CHAIN', '1') != '0'
 
 
 class FoldedMLP(object):
@@ -72,9 +77,40 @@ class FoldedMLP(object):
         self._tag, self._layers = tag, layers
         return layers
 
-    def __call__(self, x, dtype):
-        """x: [N, C] fp32.  The first layer runs in fp32 (raw metric coordinates do not survive a bf16 cast), the rest
-        in ``dtype``."""
+    def _chain(self, x):
+        """The folded layers as one os3d_mlp_chain_bf16 launch (activations on chip), or None when the chain does not fit
+        the kernel.  An fp32 input goes through the kernel's fp32 front layer (raw metric coordinates do not survive a
+        bf16 cast)."""
+        layers = self._build()
+        key = (self._tag, x.dtype)
+        hit = self.__dict__.get('_chain_hit')
+        if hit is None or hit[0] != key:
+            chain = None
+            spec = [(w, b, RELU if relu else NONE) for w, b, relu, _ in layers]
+            front = None
+            if x.dtype == torch.float32:
+                front, spec = spec[0], spec[1:]
+                if front[0].shape[0] != 64 or front[0].shape[1] > 16:
+                    spec = []
+            if 2 <= len(spec) <= 4 and MlpChain.fits([tuple(w.shape) for w, _, _ in spec], front is not None):
+                chain = MlpChain(spec, front=front)
+            hit = self.__dict__['_chain_hit'] = (key, chain)
+        return hit[1]
+
+    def __call__(self, x, dtype, out=None):
+        """x: [N, C] fp32 or bf16.  The first layer of an fp32 input runs in fp32, the rest in ``dtype``.  ``out``:
+        optional preallocated destination (a column slice of a wider buffer) for the bf16 chain kernel."""
+        if dtype == torch.bfloat16 and _USE_MLP_CHAIN and x.dtype in (torch.float32, torch.bfloat16):
+            chain = self._chain(x)
+            if chain is not None:
+                return chain(x, out=out)
+        y = self._layerwise(x, dtype)
+        if out is not None:
+            out.copy_(y)
+            return out
+        return y
+
+    def _layerwise(self, x, dtype):
         for li, (w, b, relu, cast) in enumerate(self._build()):
             dt = torch.float32 if li == 0 and x.dtype == torch.float32 else dtype
             if dt not in cast:
