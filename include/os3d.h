@@ -196,6 +196,17 @@ int os3d_mlp_chain_bf16(const void *x, int64_t m, int64_t ldx, const float *x32,
                         int64_t ldr, const float *ln_gamma, const float *ln_beta, float ln_eps, void *out, int64_t ldo,
                         int n_out, int out_f32, void *stream);
 
+/* The SWFormer MLP with its norm and residual as one persistent kernel (mlp2_tc.cu), weights streamed from L2 in chunks
+ * of the hidden dimension so that C = 192 (2 x 147 KB of weights) runs too:
+ *   out[m, c] = x + LayerNorm(fc2(GELU(fc1(x))))      x, out bf16 [m, c] contiguous; w1 / w2: os3d_pack_linear_bf16 images
+ * of fc1.weight [h, c] and fc2.weight [c, h]; exact (erf) GELU.  c % 16 == 0, c <= 192; h % 64 == 0 or h <= 128
+ * (os3d_swformer_mlp_fits).
+ * replaces: MLP + norm2 + residual of EncoderLayer.forward (seg3d/models/layers/point_transformer_layer.py:260-298). */
+int os3d_swformer_mlp_fits(int c, int h);
+int os3d_swformer_mlp_bf16(const void *x, int64_t m, int c, int h, const void *w1, const float *b1, const void *w2,
+                           const float *b2, const float *ln_gamma, const float *ln_beta, float ln_eps, void *out,
+                           void *stream);
+
 /* ---------------------------------------------------------------- stage 4: window partition + attention --- */
 
 #define OS3D_MAX_LEVELS 4

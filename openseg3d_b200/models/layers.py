@@ -20,9 +20,9 @@ from .. import _lib
 from .._lib import WindowCfg
 from ..ops.pooling import scatter_mean
 from ..ops.linear import PackedLinearCache, linear_bf16
-from ..ops.mlp_chain import GELU as MLP_GELU, NONE as MLP_NONE, MlpChain
+from ..ops.mlp_chain import GELU as MLP_GELU, NONE as MLP_NONE, MlpChain, SwformerMlp
 
-_USE_MLP_CHAIN = os.environ.get('OS3D_MLP_CHAIN', '1') != '0'
+_MLP_MODE = os.environ.get('OS3D_MLP_CHAIN', '1')
 
 
 class WindowSegments(object):
@@ -529,18 +529,23 @@ class EncoderLayer(nn.Module):
 
 
     def _mlp_chain(self):
-        """MlpChain of fc1 / GELU / fc2 when both weight matrices fit in shared memory (C <= 96), else None.  Rebuilt when
-        a parameter changes."""
-        if not _USE_MLP_CHAIN:
+        """The fused MLP + norm2 + residual kernel for this layer, or None when its width is beyond the kernels (C > 192).
+        Rebuilt when a parameter changes.  OS3D_MLP_CHAIN: 1 (default) = weights streamed (os3d_swformer_mlp_bf16, C <= 192),
+        chain = weights resident (os3d_mlp_chain_bf16, C <= 96), 0 = unfused."""
+        if _MLP_MODE == '0':
             return None
         fc1, fc2 = self.mlp.fc1, self.mlp.fc2
         tag = tuple((t.data_ptr(), t._version) for t in (fc1.weight, fc1.bias, fc2.weight, fc2.bias))
         hit = self.__dict__.get('_chain')
         if hit is None or hit[0] != tag:
-            chain = None
-            if MlpChain.fits([tuple(fc1.weight.shape), tuple(fc2.weight.shape)]):
-                chain = MlpChain([(fc1.weight, fc1.bias, MLP_GELU), (fc2.weight, fc2.bias, MLP_NONE)])
-            hit = self.__dict__['_chain'] = (tag, chain)
+            fn = None
+            h, c = fc1.weight.shape
+            if _MLP_MODE != 'chain' and SwformerMlp.fits(c, h):
+                mlp = SwformerMlp(fc1.weight, fc1.bias, fc2.weight, fc2.bias)
+                fn = lambda x, residual, ln: mlp(x, ln)                      # noqa: E731  (the residual is x itself)
+            elif MlpChain.fits([(h, c), (c, h)]):
+                fn = MlpChain([(fc1.weight, fc1.bias, MLP_GELU), (fc2.weight, fc2.bias, MLP_NONE)])
+            hit = self.__dict__['_chain'] = (tag, fn)
         return hit[1]
 
 

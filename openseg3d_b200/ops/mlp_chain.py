@@ -106,3 +106,32 @@ class MlpChain(object):
                                          m * (x.shape[1] * x.element_size() + self.n_out * out.element_size()
                                               + (self.n_out * 2 if residual is not None else 0))))
         return out
+
+
+class SwformerMlp(object):
+    """out = x + LayerNorm(fc2(GELU(fc1(x)))) as one kernel with the hidden tensor on chip and the weights streamed from L2
+    (os3d_swformer_mlp_bf16, csrc/mlp2_tc.cu); C <= 192."""
+
+    def __init__(self, w1, b1, w2, b2):
+        self.h, self.c = w1.shape
+        if tuple(w2.shape) != (self.c, self.h) or not self.fits(self.c, self.h):
+            raise RuntimeError(f'SwformerMlp: fc1 {tuple(w1.shape)} / fc2 {tuple(w2.shape)} do not fit the kernel')
+        self.w1, self.w2 = _pack(w1.detach().float()), _pack(w2.detach().float())
+        self.b1 = None if b1 is None else b1.detach().float().contiguous()
+        self.b2 = None if b2 is None else b2.detach().float().contiguous()
+
+    @staticmethod
+    def fits(c, h):
+        return bool(_lib.lib().os3d_swformer_mlp_fits(c, h))
+
+    def __call__(self, x, ln):
+        _lib.require_cuda(x)
+        if x.dtype != torch.bfloat16 or x.dim() != 2 or x.shape[1] != self.c:
+            raise RuntimeError(f'SwformerMlp takes bfloat16 [m, {self.c}]')
+        x = x.contiguous()
+        out = torch.empty_like(x)
+        gamma, beta, eps = ln
+        m = x.shape[0]
+        _lib.call('os3d_swformer_mlp_bf16', x, m, self.c, self.h, self.w1, self.b1, self.w2, self.b2, gamma, beta, float(eps),
+                  out, work=lambda: _lib.Work(4.0 * m * self.c * self.h, 3.0 * m * self.c * 2))
+        return out

@@ -119,3 +119,27 @@ def test_rejects_what_does_not_fit():
         MlpChain(_cuda(_chain([192, 384, 192], [2, 0], 8)))
     with pytest.raises(RuntimeError):
         MlpChain(_cuda(_chain([64, 64, 64], [1, 0], 9)))(torch.randn(4, 64).cuda())      # fp32 without a front layer
+
+
+@pytest.mark.parametrize('c,m', [(48, 1), (48, 1000), (96, 129), (192, 4000), (192, 300000), (96, 250000), (48, 250000),
+                                 (64, 33000), (128, 70000)])
+def test_swformer_mlp_streamed_weights(c, m):
+    """os3d_swformer_mlp_bf16: the same operation with the weights streamed in hidden-dimension chunks (C up to 192)."""
+    from openseg3d_b200.ops.mlp_chain import SwformerMlp
+    layers = _chain([c, 2 * c, c], [2, 0], 11)
+    torch.manual_seed(12)
+    x = (torch.randn(m, c) * 1.5).bfloat16()
+    gamma, beta = torch.rand(c) + 0.5, torch.randn(c)
+    (w1, b1, _), (w2, b2, _) = layers
+    mlp = SwformerMlp(w1.cuda(), b1.cuda(), w2.cuda(), b2.cuda())
+    y = mlp(x.cuda(), (gamma.cuda(), beta.cuda(), 1e-5))
+    assert y.shape == (m, c) and y.dtype == torch.bfloat16
+    _check(y, _ref(x, layers, residual=x, ln=(gamma, beta, 1e-5)))
+
+
+def test_swformer_mlp_rejects_wide_layers():
+    from openseg3d_b200.ops.mlp_chain import SwformerMlp
+    assert not SwformerMlp.fits(384, 768)
+    assert SwformerMlp.fits(192, 384)
+    with pytest.raises(RuntimeError):
+        SwformerMlp(torch.zeros(768, 384).cuda(), None, torch.zeros(384, 768).cuda(), None)

@@ -45,3 +45,13 @@ for name, widths, acts, m, front in cases:
     ms = timeit(lambda: c(x, **kw))
     byts = m * (x.shape[1] * x.element_size() + widths[-1] * 2 * (2 if kw else 1))
     print(f'{name:40s} m={m:8d} {ms:7.3f} ms  {c.flops_per_row * m / ms / 1e9:8.1f} TFLOP/s  {byts / ms / 1e6:7.1f} GB/s', flush=True)
+
+from openseg3d_b200.ops.mlp_chain import SwformerMlp  # noqa: E402
+for c, m in ((48, 932000), (96, 1020000), (192, 467000)):
+    mlp = SwformerMlp(torch.randn(2 * c, c, device='cuda') / c ** 0.5, torch.randn(2 * c, device='cuda'),
+                      torch.randn(c, 2 * c, device='cuda') / (2 * c) ** 0.5, torch.randn(c, device='cuda'))
+    x = torch.randn(m, c, device='cuda').bfloat16()
+    ln = (torch.ones(c, device='cuda'), torch.zeros(c, device='cuda'), 1e-5)
+    ms = timeit(lambda: mlp(x, ln))
+    print(f'swformer mlp (streamed weights) C={c:3d}      m={m:8d} {ms:7.3f} ms  {8.0 * m * c * c / ms / 1e9:8.1f} TFLOP/s  '
+          f'{3 * m * c * 2 / ms / 1e6:7.1f} GB/s', flush=True)
