@@ -260,14 +260,19 @@ def main():
             'achieved_tflops': round(at[1] / (at[0] * 1e-3) / 1e12, 1),
             'frac_of_tensor_peak': round(at[1] / (at[0] * 1e-3) / 1e12 / pk['tensor'], 4),
             'note': 'instruction bound in the softmax (ncu: profiles/r01c_attention_l2_full.txt), not by the tensor pipe'}
-    # the persistent Linear kernel (linear_tc_kernel: out-proj/fc2 + residual + LayerNorm, table-mode q|k projection): its
-    # tensor work is small next to its activations, so HBM bounds it -- bytes = x + out (+ residual) + weights (+ row ids)
-    lt = by.get('os3d_linear_tc_bf16')
-    if lt and lt[0]:
-        roofline['linear_tc_kernel'] = {
-            'ms': round(lt[0], 3), 'launches_per_step': lt[2], 'algorithmic_mb': round(lt[3] / 1e6, 1),
-            'achieved_gbs': round(lt[3] / (lt[0] * 1e-3) / 1e9, 1), 'frac_of_hbm_peak': round(lt[3] / (lt[0] * 1e-3) / 1e9 / pk['hbm'], 3),
-            'achieved_tflops': round(lt[1] / (lt[0] * 1e-3) / 1e12, 1)}
+    # the persistent dense kernels of the SWFormer layers and the point MLPs (linear_tc_kernel: out-proj + residual +
+    # LayerNorm, level-4 fc2; swformer_mlp_tc_kernel: fc1 + GELU + fc2 + LayerNorm + residual with the hidden tensor on
+    # chip; mlp_chain_tc_kernel: the BatchNorm-folded point MLPs).  Their tensor work is small next to their activations,
+    # so HBM is the roofline: bytes = inputs + outputs (+ residual) (+ weights once)
+    for entry, key in (('os3d_linear_tc_bf16', 'linear_tc_kernel'), ('os3d_swformer_mlp_bf16', 'swformer_mlp_tc_kernel'),
+                       ('os3d_mlp_chain_bf16', 'mlp_chain_tc_kernel')):
+        lt = by.get(entry)
+        if lt and lt[0]:
+            roofline[key] = {
+                'ms': round(lt[0], 3), 'launches_per_step': lt[2], 'algorithmic_mb': round(lt[3] / 1e6, 1),
+                'achieved_gbs': round(lt[3] / (lt[0] * 1e-3) / 1e9, 1),
+                'frac_of_hbm_peak': round(lt[3] / (lt[0] * 1e-3) / 1e9 / pk['hbm'], 3),
+                'achieved_tflops': round(lt[1] / (lt[0] * 1e-3) / 1e12, 1)}
 
     line = {'metric': 'points/sec, Waymo 1-sweep seg forward', 'value': value, 'unit': 'points/s', 'n_gpus': world,
             'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': total_ms / args.steps, 'higher_is_better': True,
