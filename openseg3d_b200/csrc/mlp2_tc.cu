@@ -12,7 +12,7 @@
 //   * MMA 1 runs two chunks ahead of MMA 2 (two acc1 buffers, each handed back right after the epilogue warps' tcgen05.ld
 //     of it), so its result is ready when the epilogue warps finish the chunk before;
 //   * h has two buffers; MMA 2 (c) only has to finish before the epilogue of chunk c+2 writes its buffer again;
-//   * acc2 has two buffers and the LayerNorm epilogue of tile t runs after the first hidden chunk of tile t+1.
+//   * acc2 has two buffers and the LayerNorm epilogue of tile t runs after the second hidden chunk of tile t+1.
 //
 //   * W1 and W2 chunks travel through separate rings: a W1 stage is free as soon as MMA 1 has read it (a chunk before
 //     MMA 2 of the same chunk), so the next W1 copy -- the one on the critical path -- starts a whole chunk earlier than
@@ -37,6 +37,9 @@ constexpr int kBlkBytes = kTileM * 128;
 constexpr int kEpiWarps = 16;                   // 4 per TMEM lane quarter: the epilogue math (GELU, LayerNorm) is what bounds the kernel
 constexpr int kThreads = (kEpiWarps + 3) * 32;
 constexpr int kMaxStages = 4;
+constexpr int kStageRow = 144;                  // staging row: 128 bytes of a 64-column block + 16 (bank stagger)
+constexpr int kStageQBytes = 32 * kStageRow;    // per TMEM lane quarter
+constexpr int kStageBytes = 4 * kStageQBytes;
 
 struct alignas(64) Params {
   CUtensorMap tmap_x;               // x [m, c] bf16, box {64, 128}, SWIZZLE_128B
@@ -82,7 +85,8 @@ __global__ void __launch_bounds__(kThreads, 1) swformer_mlp_tc_kernel(const __gr
   const uint32_t w2_base = w1_base + p.s1 * p.w1_bytes;
   const uint32_t h_base = w2_base + p.s2 * p.w2_bytes;
   uint8_t *h_ptr = smem + (h_base - base);
-  uint8_t *tail = smem + (h_base - base) + 2u * h_bytes;
+  uint8_t *stage_ptr = smem + (h_base - base) + 2u * h_bytes;        // epilogue staging (kStageBytes)
+  uint8_t *tail = stage_ptr + kStageBytes;
   uint64_t *bars = reinterpret_cast<uint64_t *>(tail);
   // x_full[2] x_empty[2] acc1_full[2] h_ready[2] h_free[2] acc2_full[2] acc2_free[2] w1_full[4] w1_free[4] w2_full[4] w2_free[4]
   const uint32_t x_full = smem_u32(bars), x_empty = smem_u32(bars + 2), acc1_full = smem_u32(bars + 4);
@@ -270,21 +274,27 @@ __global__ void __launch_bounds__(kThreads, 1) swformer_mlp_tc_kernel(const __gr
     // LayerNorm + residual epilogue of tile t.  A warp owns at most three 16-column chunks (c <= 192): they stay in
     // registers between the statistics and the normalisation, the residual rows are requested before the accumulator
     // is waited for, and the accumulator is handed back as soon as it has been read.
+    // Global traffic of the LayerNorm epilogue goes through a small staging buffer per lane quarter (32 rows x one
+    // 64-column block, rows padded to 144 bytes): a thread owns a ROW of the accumulator, so direct loads / stores touch 32
+    // different 128-byte lines per instruction -- the clock64 trace put 6300 of the 8350 cycles of this epilogue there
+    // (l1tex tag stage, not bytes).  Staged, 8 lanes cover one row's 128 bytes: 4 lines per instruction.
+    uint8_t *stq = stage_ptr + quarter * kStageQBytes;
+    const int g = cpart * 32 + lane;                     // thread index within the quarter's four warps
     auto final_epilogue = [&](int t) {
       const uint32_t ab = (uint32_t)t & 1u;
-      const int64_t row = (int64_t)((int)blockIdx.x + t * (int)gridDim.x) * kTileM + r;
-      const bool row_ok = row < p.m;
+      const int64_t row0q = (int64_t)((int)blockIdx.x + t * (int)gridDim.x) * kTileM + quarter * 32;
       const uint32_t t_row = tmem_base + (uint32_t)p.acc2_base + ab * (uint32_t)p.c + lane_sel;
-      const __nv_bfloat16 *rrow = p.x + row * p.c;
+      // this thread's two 16-byte pieces of every 32-row x 64-column block: (row, piece) = (g / 8, g % 8), (g / 8 + 16, g % 8)
+      const int prow = g >> 3, piece = g & 7;
       uint4 rz[3][2];
       if (warp == 0) TRACE(2, t, 0);
 #pragma unroll
       for (int i = 0; i < 3; ++i) {
-        const int col = cpart * 16 + 64 * i;
         rz[i][0] = rz[i][1] = make_uint4(0, 0, 0, 0);
-        if (col < p.c && row_ok) {
-          rz[i][0] = __ldg(reinterpret_cast<const uint4 *>(rrow + col));
-          rz[i][1] = __ldg(reinterpret_cast<const uint4 *>(rrow + col) + 1);
+        const int col = 64 * i + piece * 8;
+        if (col < p.c) {
+          if (row0q + prow < p.m) rz[i][0] = __ldg(reinterpret_cast<const uint4 *>(p.x + (row0q + prow) * p.c + col));
+          if (row0q + prow + 16 < p.m) rz[i][1] = __ldg(reinterpret_cast<const uint4 *>(p.x + (row0q + prow + 16) * p.c + col));
         }
       }
       mbar_wait(acc2_full + 8 * ab, ((uint32_t)t >> 1) & 1u);
@@ -331,24 +341,31 @@ __global__ void __launch_bounds__(kThreads, 1) swformer_mlp_tc_kernel(const __gr
         sum += o2.x;
         sq += o2.y;
       }
-      asm volatile("bar.sync %0, 128;" ::"r"(1 + quarter) : "memory");
       if (warp == 0) TRACE(2, t, 5);
       const float mean = sum / (float)p.c;
       const float rstd = rsqrtf(fmaxf(sq / (float)p.c - mean * mean, 0.0f) + p.ln_eps);
 #pragma unroll
       for (int i = 0; i < 3; ++i) {
+        if (64 * i >= p.c) break;
         const int col = cpart * 16 + 64 * i;
-        if (col < p.c && row_ok) {
+        // residual block -> staging (also orders the previous block's reads / the statistics exchange before the writes)
+        asm volatile("bar.sync %0, 128;" ::"r"(1 + quarter) : "memory");
+        *reinterpret_cast<uint4 *>(stq + prow * kStageRow + piece * 16) = rz[i][0];
+        *reinterpret_cast<uint4 *>(stq + (prow + 16) * kStageRow + piece * 16) = rz[i][1];
+        asm volatile("bar.sync %0, 128;" ::"r"(1 + quarter) : "memory");
+        if (col < p.c) {
 #pragma unroll
           for (int q4 = 0; q4 < 4; ++q4) {
-            const float4 g = *reinterpret_cast<const float4 *>(prm_s + o_g + col + 4 * q4);
+            const float4 g4 = *reinterpret_cast<const float4 *>(prm_s + o_g + col + 4 * q4);
             const float4 be = *reinterpret_cast<const float4 *>(prm_s + o_be + col + 4 * q4);
-            const float gg[4] = {g.x, g.y, g.z, g.w}, eb[4] = {be.x, be.y, be.z, be.w};
+            const float gg[4] = {g4.x, g4.y, g4.z, g4.w}, eb[4] = {be.x, be.y, be.z, be.w};
 #pragma unroll
             for (int e = 0; e < 4; ++e)
               v[i][4 * q4 + e] = __float_as_uint(fmaf((__uint_as_float(v[i][4 * q4 + e]) - mean) * rstd, gg[e], eb[e]));
           }
-          const uint32_t rw[8] = {rz[i][0].x, rz[i][0].y, rz[i][0].z, rz[i][0].w, rz[i][1].x, rz[i][1].y, rz[i][1].z, rz[i][1].w};
+          uint4 *mine = reinterpret_cast<uint4 *>(stq + lane * kStageRow + cpart * 32);
+          const uint4 r0 = mine[0], r1 = mine[1];
+          const uint32_t rw[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
           uint32_t o[8];
 #pragma unroll
           for (int k = 0; k < 8; ++k) {
@@ -356,14 +373,23 @@ __global__ void __launch_bounds__(kThreads, 1) swformer_mlp_tc_kernel(const __gr
                                                             __uint_as_float(v[i][2 * k + 1]) + __uint_as_float(rw[k] & 0xffff0000u));
             o[k] = *reinterpret_cast<const uint32_t *>(&hh);
           }
-          __nv_bfloat16 *dst = p.out + row * p.c + col;
-          reinterpret_cast<uint4 *>(dst)[0] = make_uint4(o[0], o[1], o[2], o[3]);
-          reinterpret_cast<uint4 *>(dst)[1] = make_uint4(o[4], o[5], o[6], o[7]);
+          mine[0] = make_uint4(o[0], o[1], o[2], o[3]);
+          mine[1] = make_uint4(o[4], o[5], o[6], o[7]);
+        }
+        asm volatile("bar.sync %0, 128;" ::"r"(1 + quarter) : "memory");
+        const int ocol = 64 * i + piece * 8;
+        if (ocol < p.c) {
+          if (row0q + prow < p.m)
+            *reinterpret_cast<uint4 *>(p.out + (row0q + prow) * p.c + ocol) = *reinterpret_cast<const uint4 *>(stq + prow * kStageRow + piece * 16);
+          if (row0q + prow + 16 < p.m)
+            *reinterpret_cast<uint4 *>(p.out + (row0q + prow + 16) * p.c + ocol) =
+                *reinterpret_cast<const uint4 *>(stq + (prow + 16) * kStageRow + piece * 16);
         }
         if (warp == 0) TRACE(2, t, 6 + (i > 0));
       }
     };
 
+    const int jf = p.nj > 1 ? 1 : 0;              // the chunk of tile t after which tile t - 1 gets its LayerNorm epilogue
     for (int c = 0, t = 0, j = 0; c < n_chunks; ++c, j = (j + 1 == p.nj ? 0 : j + 1), t += (j == 0)) {
       const uint32_t s = (uint32_t)c & 1u;
       if (warp == 0) TRACE(0, c, 0);
@@ -409,8 +435,8 @@ __global__ void __launch_bounds__(kThreads, 1) swformer_mlp_tc_kernel(const __gr
       __syncwarp();
       if (lane == 0) mbar_arrive(h_ready + 8 * s);
       if (warp == 0) TRACE(0, c, 5);
-      if (j == 0 && t >= 1) final_epilogue(t - 1);
-      if (warp == 0) TRACE(0, c, 6);      // deferred: MMA 2 of the previous tile's last chunk has long finished
+      if (j == jf && t >= 1) final_epilogue(t - 1);     // deferred: MMA 2 of the previous tile's last chunk has long finished
+      if (warp == 0) TRACE(0, c, 6);
     }
     if (n_my > 0) final_epilogue(n_my - 1);
   }
@@ -463,7 +489,7 @@ static Plan plan(int c, int h) {
   pl.tail = 32 * 8 + 16 + kEpiWarps * 32 * 8 + (h + 3 * c) * 4 + 64;
   const int x_bytes = pl.ncb_c * kBlkBytes, limit = 227 * 1024;
   auto total = [&](int xb, int s1, int s2) {
-    return 1024 + xb * x_bytes + s1 * (int)pl.w1_bytes + s2 * (int)pl.w2_bytes + 2 * pl.ncb_hc * kBlkBytes + pl.tail;
+    return 1024 + xb * x_bytes + s1 * (int)pl.w1_bytes + s2 * (int)pl.w2_bytes + 2 * pl.ncb_hc * kBlkBytes + kStageBytes + pl.tail;
   };
   if (total(1, 2, 2) > limit) return pl;
   pl.xb = 1; pl.s1 = 2; pl.s2 = 2;

@@ -177,7 +177,7 @@ __global__ void __launch_bounds__(kSortWarps * 32) win_sort_kernel(const int64_t
   for (int t = lane; t < n; t += 32) pos_seg[off + t] = make_int2(off, n);  // (window start, length) per position
   const int cap = cfg.lvl_tokens[lvl];
   int dropped = 0;
-  if (n <= kMaxSeg) {
+  if (n <= 64) {
     for (int t = lane; t < n; t += 32) buf[wid][t] = seg[t];
     __syncwarp();
     for (int t = lane; t < n; t += 32) {
@@ -189,6 +189,34 @@ __global__ void __launch_bounds__(kSortWarps * 32) win_sort_kernel(const int64_t
       win_rank[mine] = slot - first_of_level;
       inner[mine] = r;
       dropped += r >= cap;
+    }
+  } else if (n <= kMaxSeg) {
+    // larger windows: bitonic sort of the (unique) voxel rows in shared memory -- O(n log^2 n / 32) steps for the warp
+    // instead of the O(n^2 / 32) of rank counting, which made the few 500-800 token windows of the coarse levels the
+    // critical path of the whole launch (one warp, 20k iterations)
+    int pow2 = 128;
+    while (pow2 < n) pow2 <<= 1;
+    int32_t *b = buf[wid];
+    for (int t = lane; t < pow2; t += 32) b[t] = t < n ? seg[t] : 0x7fffffff;
+    __syncwarp();
+    for (int k = 2; k <= pow2; k <<= 1) {
+      for (int j = k >> 1; j > 0; j >>= 1) {
+        for (int i = lane; i < (pow2 >> 1); i += 32) {
+          const int lo = ((i & ~(j - 1)) << 1) | (i & (j - 1)), hi = lo | j;
+          const int32_t x = b[lo], y = b[hi];
+          const bool up = (lo & k) == 0;
+          if ((x > y) == up) { b[lo] = y; b[hi] = x; }
+        }
+        __syncwarp();
+      }
+    }
+    for (int t = lane; t < n; t += 32) {
+      const int32_t mine = b[t];
+      seg[t] = mine;
+      level[mine] = lvl;
+      win_rank[mine] = slot - first_of_level;
+      inner[mine] = t;
+      dropped += t >= cap;
     }
   } else {  // longer than the staging buffer (never for windows: max_tokens <= 800): rank straight from global
             // memory; the segment itself stays in arrival order (attention is order independent)
