@@ -272,15 +272,25 @@ class SparseInverseConv3d(_SparseConvBase):
 
 
 def bn_scale_shift(bn, conv_bias=None):
-    """Eval-mode BatchNorm1d (and the conv bias before it) as y = acc * scale + shift, in fp32."""
-    inv = torch.rsqrt(bn.running_var.float() + bn.eps)
-    scale = inv * bn.weight.float() if bn.affine else inv
-    shift = -bn.running_mean.float() * scale
-    if bn.affine:
-        shift = shift + bn.bias.float()
-    if conv_bias is not None:
-        shift = shift + conv_bias.float() * scale
-    return scale.contiguous(), shift.contiguous()
+    """Eval-mode BatchNorm1d (and the conv bias before it) as y = acc * scale + shift, in fp32.  Cached on the module and
+    recomputed only when a parameter or running statistic changes (seven tiny kernels per conv per forward otherwise)."""
+    srcs = [bn.running_var, bn.running_mean] + ([bn.weight, bn.bias] if bn.affine else []) + \
+           ([conv_bias] if conv_bias is not None else [])
+    tag = tuple((t.data_ptr(), t._version) for t in srcs)
+    hit = bn.__dict__.get('_os3d_fold')
+    if hit is not None and hit[0] == tag:
+        return hit[1]
+    with torch.no_grad():
+        inv = torch.rsqrt(bn.running_var.float() + bn.eps)
+        scale = inv * bn.weight.float() if bn.affine else inv
+        shift = -bn.running_mean.float() * scale
+        if bn.affine:
+            shift = shift + bn.bias.float()
+        if conv_bias is not None:
+            shift = shift + conv_bias.float() * scale
+        out = (scale.contiguous(), shift.contiguous())
+    bn.__dict__['_os3d_fold'] = (tag, out)
+    return out
 
 
 class SparseSequential(SparseModule):
