@@ -219,7 +219,7 @@ def main():
     # launches in a step (2 * pairs * Cin * Cout per conv, recomputed from the live kernel maps; 2 * M * K * N per
     # Linear) / their CUDA-event time.  traffic = DRAM bytes per launch from the committed ncu launch list.
     if dtype == torch.bfloat16:
-        entries = ['os3d_spconv_fwd_bf16', 'os3d_linear_bf16']
+        entries = ['os3d_spconv_fwd_bf16_ld', 'os3d_spconv_fwd_bf16', 'os3d_linear_bf16']
         kname = 'spconv_tc_kernel (tcgen05 gather-GEMM: sparse conv + LayerNorm-fused Linear)'
     else:
         entries = ['os3d_spconv_fwd_f32']

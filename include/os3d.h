@@ -143,6 +143,12 @@ int os3d_kernel_map_tiles(const int32_t *nbr, int64_t m, const int32_t *perm, in
 int os3d_spconv_fwd_bf16(const void *in, int64_t m_in, const int32_t *nbr_t, const uint32_t *tile_mask,
                          const int32_t *perm, int64_t m_out, int cin, int cout, const void *w, const float *scale,
                          const float *shift, const void *residual, int flags, void *out, void *stream);
+/* The same with an output row pitch `ldo` (elements, >= cout, multiple of 8): the rows of `out` may be a column slice of a
+ * wider row-major buffer -- the decoder writes both halves of torch.cat([x_bottom, x_trans]) (pointtransformer.py:105)
+ * straight into one buffer instead of concatenating. */
+int os3d_spconv_fwd_bf16_ld(const void *in, int64_t m_in, const int32_t *nbr_t, const uint32_t *tile_mask,
+                            const int32_t *perm, int64_t m_out, int cin, int cout, const void *w, const float *scale,
+                            const float *shift, const void *residual, int flags, void *out, int64_t ldo, void *stream);
 /* spconv 2.x weight [cout, kz, ky, kx, cin] f32 -> kernel layouts.  f32: [27, cin, cout].  bf16: the shared-memory image
  * of the UMMA B operand, [27 * ceil(cin/64)][cout][128 B swizzled] (os3d_spconv_bf16_packed_elems elements). */
 int os3d_spconv_bf16_packed_elems(int cin, int cout, int64_t *elems);

@@ -631,11 +631,13 @@ static int launch_tc(tc::Params &p, cudaStream_t stream) {
   return 0;
 }
 
-extern "C" int os3d_spconv_fwd_bf16(const void *in, int64_t m_in, const int32_t *nbr_t, const uint32_t *tile_mask,
-                                    const int32_t *perm, int64_t m_out, int cin, int cout, const void *w, const float *scale,
-                                    const float *shift, const void *residual, int flags, void *out, void *stream) {
+extern "C" int os3d_spconv_fwd_bf16_ld(const void *in, int64_t m_in, const int32_t *nbr_t, const uint32_t *tile_mask,
+                                       const int32_t *perm, int64_t m_out, int cin, int cout, const void *w,
+                                       const float *scale, const float *shift, const void *residual, int flags, void *out,
+                                       int64_t ldo, void *stream) {
   if (cin <= 0 || cin % 8 || cout < 16 || cout % 16 || cout > 512 || (cout > 256 && cout % 32) ||
-      ((scale == nullptr) != (shift == nullptr)) || m_in <= 0 || ((uintptr_t)in & 15))
+      ((scale == nullptr) != (shift == nullptr)) || m_in <= 0 || ((uintptr_t)in & 15) || ldo < cout || ldo % 8 ||
+      ((uintptr_t)out & 15))
     return OS3D_ERR_BAD_ARG;
   if (m_out == 0) return 0;
   tc::Params p;
@@ -656,7 +658,7 @@ extern "C" int os3d_spconv_fwd_bf16(const void *in, int64_t m_in, const int32_t 
   p.residual = (const __nv_bfloat16 *)residual;
   p.flags = flags;
   p.out = (__nv_bfloat16 *)out;
-  p.ldo = cout;
+  p.ldo = ldo;
   p.dense = 0;
   p.ln_gamma = p.ln_beta = nullptr;
   p.ln_eps = 0.0f;
@@ -664,6 +666,13 @@ extern "C" int os3d_spconv_fwd_bf16(const void *in, int64_t m_in, const int32_t 
   p.tab_idx = nullptr;
   p.tab_cols = 0;
   return launch_tc(p, (cudaStream_t)stream);
+}
+
+extern "C" int os3d_spconv_fwd_bf16(const void *in, int64_t m_in, const int32_t *nbr_t, const uint32_t *tile_mask,
+                                    const int32_t *perm, int64_t m_out, int cin, int cout, const void *w, const float *scale,
+                                    const float *shift, const void *residual, int flags, void *out, void *stream) {
+  return os3d_spconv_fwd_bf16_ld(in, m_in, nbr_t, tile_mask, perm, m_out, cin, cout, w, scale, shift, residual, flags, out,
+                                 cout, stream);
 }
 
 extern "C" int os3d_linear_bf16_packed_elems(int k, int n, int64_t *elems) {

@@ -56,12 +56,13 @@ class SparseBasicBlock(spconv.SparseModule):
                                        indice_key=indice_key)
         self.bn2 = norm_fn(planes)
 
-    def forward(self, x):
+    def forward(self, x, out=None):
+        """``out`` (inference only): destination view for the block's output features."""
         if not self.training and not torch.is_grad_enabled():   # inference: BN, residual add and ReLU live in the conv epilogues
             s1, b1 = bn_scale_shift(self.bn1, self.conv1.bias)
             s2, b2 = bn_scale_shift(self.bn2, self.conv2.bias)
-            out = self.conv1(x, scale=s1, shift=b1, relu=True)
-            return self.conv2(out, scale=s2, shift=b2, residual=x.features, relu=True)
+            mid = self.conv1(x, scale=s1, shift=b1, relu=True)
+            return self.conv2(mid, scale=s2, shift=b2, residual=x.features, relu=True, out=out)
         out = self.conv1(x)
         out = replace_feature(out, self.act(self.bn1(out.features)))
         out = self.conv2(out)
@@ -95,13 +96,27 @@ class UpBlock(spconv.SparseModule):
         assert (in_channels % out_channels == 0) and (in_channels >= out_channels)
         return replace_feature(x, features.view(n, out_channels, -1).sum(dim=2))
 
+    feeds_upblock = False      # set by PointTransformer: the next decoder block concatenates this block's output
+
     def forward(self, x_bottom, x_lateral):
-        x_trans = self.transform(x_lateral)
-        x = replace_feature(x_trans, torch.cat([x_bottom.features, x_trans.features], dim=1))
-        if not self.training and not torch.is_grad_enabled():   # inference: BN + ReLU + channel_reduction(cat) + add in the bottleneck's epilogue
+        if not self.training and not torch.is_grad_enabled():
+            # inference: no torch.cat -- x_bottom already sits in the left half of a double-width buffer (written there by
+            # the previous block's `out` conv; copied once at level 4, where it is the encoder output) and the transform
+            # block writes its result into the right half; BN + ReLU + channel_reduction(cat) + add run in the
+            # bottleneck's epilogue
+            c = x_bottom.features.shape[1]
+            wide = getattr(x_bottom, '_os3d_wide', None)
+            if wide is None or wide.shape[0] != x_lateral.features.shape[0] or wide.dtype != x_lateral.features.dtype:
+                wide = torch.empty((x_bottom.features.shape[0], 2 * c), dtype=x_lateral.features.dtype,
+                                   device=x_bottom.features.device)
+                wide[:, :c] = x_bottom.features
+            x_trans = self.transform(x_lateral, out=wide[:, c:])
+            x = replace_feature(x_trans, wide)
             conv, bn = self.bottleneck[0], self.bottleneck[1]
             scale, shift = bn_scale_shift(bn, conv.bias)
-            return self.out(conv(x, scale=scale, shift=shift, residual=x.features, relu=3))
+            return self.out(conv(x, scale=scale, shift=shift, residual=x.features, relu=3), wide_out=self.feeds_upblock)
+        x_trans = self.transform(x_lateral)
+        x = replace_feature(x_trans, torch.cat([x_bottom.features, x_trans.features], dim=1))
         x_m = self.bottleneck(x)
         x = self.channel_reduction(x, x_m.features.shape[1])
         x = replace_feature(x, x_m.features + x.features)
@@ -143,6 +158,7 @@ class PointTransformer(nn.Module):
         self.up3 = UpBlock(192, 96, self.norm_fn, self.act_fn, conv_type='inverseconv', layer_id=3)
         self.up2 = UpBlock(96, 48, self.norm_fn, self.act_fn, conv_type='inverseconv', layer_id=2)
         self.up1 = UpBlock(48, output_channels, self.norm_fn, self.act_fn, conv_type='subm', layer_id=1)
+        self.up4.feeds_upblock = self.up3.feeds_upblock = self.up2.feeds_upblock = True
 
         self.aux_voxel_classifier = nn.Sequential(nn.Linear(384, num_classes, bias=False))
         self.voxel_classifier = nn.Sequential(nn.Linear(output_channels, num_classes, bias=False))

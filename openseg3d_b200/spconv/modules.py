@@ -24,17 +24,22 @@ def _triple(v):
     return tuple(v) if isinstance(v, (list, tuple)) else (v, v, v)
 
 
-def sparse_conv_forward(features, nbr, weight, bias, packed_cache, scale=None, shift=None, residual=None, relu=False):
+def sparse_conv_forward(features, nbr, weight, bias, packed_cache, scale=None, shift=None, residual=None, relu=False,
+                        out=None):
     """out[r] = epilogue( sum_k features[nbr[r, k]] @ W[:, k, :].T ).
 
     fp32 features -> exact FP32-pipe kernel (+ torch epilogue); bf16 features -> tcgen05 kernel with the epilogue
     (scale/shift = folded bias + BatchNorm, residual, ReLU) fused.  ``relu`` is the C ABI's flag word: bit 0 = ReLU,
-    bit 1 = ``residual`` has 2*cout channels and residual[:, 2c] + residual[:, 2c+1] is added after the ReLU."""
+    bit 1 = ``residual`` has 2*cout channels and residual[:, 2c] + residual[:, 2c+1] is added after the ReLU.
+    ``out``: optional destination [m_out, cout] with unit column stride -- e.g. one half of a wider row-major buffer."""
     _lib.require_cuda(features, nbr)
     features = features.contiguous()
     m_out, cout, cin = nbr.shape[0], weight.shape[0], weight.shape[-1]
     if features.shape[1] != cin:
         raise RuntimeError(f'sparse conv: features have {features.shape[1]} channels, weight expects {cin}')
+    dst = out
+    if dst is not None and (tuple(dst.shape) != (m_out, cout) or dst.stride(1) != 1 or dst.dtype != features.dtype):
+        raise RuntimeError('sparse conv: bad output buffer')
     if features.dtype == torch.float32:
         w = packed_cache.get('f32', weight)
         out = torch.empty((m_out, cout), dtype=torch.float32, device=features.device)
@@ -49,6 +54,9 @@ def sparse_conv_forward(features, nbr, weight, bias, packed_cache, scale=None, s
             out = F.relu_(out)
         if residual is not None and flags & 2:       # UpBlock: + channel_reduction(residual) after the ReLU
             out = out + residual.view(m_out, cout, 2).sum(dim=2)
+        if dst is not None:
+            dst.copy_(out)
+            return dst
         return out
     if features.dtype == torch.bfloat16:
         w, cin_pad = packed_cache.get('bf16', weight)
@@ -56,13 +64,13 @@ def sparse_conv_forward(features, nbr, weight, bias, packed_cache, scale=None, s
             features = F.pad(features, (0, cin_pad - cin))
         if scale is None and bias is not None:
             scale, shift = torch.ones_like(bias, dtype=torch.float32), bias.float()
-        out = torch.empty((m_out, cout), dtype=torch.bfloat16, device=features.device)
+        out = dst if dst is not None else torch.empty((m_out, cout), dtype=torch.bfloat16, device=features.device)
         if m_out == 0 or features.shape[0] == 0:
             return out.zero_()
         nbr_t, tile_mask, perm = kernel_map_tiles(nbr)
-        _lib.call('os3d_spconv_fwd_bf16', features, features.shape[0], nbr_t, tile_mask, perm, m_out, cin_pad, cout, w, scale,
-                  shift, residual.contiguous() if residual is not None else None, int(relu), out,
-                  work=lambda: 2.0 * cin * cout * int((nbr >= 0).sum().item()))
+        _lib.call('os3d_spconv_fwd_bf16_ld', features, features.shape[0], nbr_t, tile_mask, perm, m_out, cin_pad, cout, w,
+                  scale, shift, residual.contiguous() if residual is not None else None, int(relu),
+                  _lib._Raw(out.data_ptr()), out.stride(0), work=lambda: 2.0 * cin * cout * int((nbr >= 0).sum().item()))
         return out
     raise RuntimeError(f'sparse conv: unsupported feature dtype {features.dtype}')
 
@@ -202,17 +210,28 @@ class _SparseConvBase(SparseModule):
                 f'padding={self.padding}, bias={self.bias is not None}, indice_key={self.indice_key}')
 
     # subclasses: _table(x) -> (nbr, out SparseConvTensor prototype); _table_bwd(x) -> (map of the transposed conv, mirror)
-    def forward(self, x, scale=None, shift=None, residual=None, relu=False):
+    def forward(self, x, scale=None, shift=None, residual=None, relu=False, out=None, wide_out=False):
+        """``out``: destination view for the features (inference).  ``wide_out``: allocate a [m_out, 2 * cout] buffer, write
+        the features into its left half and hang the buffer on the result as ``_os3d_wide`` -- the decoder block that
+        consumes this tensor as x_bottom writes its lateral branch into the right half instead of torch.cat."""
         nbr, out_proto = self._table(x)
+        wide = None
+        if wide_out and out is None and not torch.is_grad_enabled():
+            wide = torch.empty((nbr.shape[0], 2 * self.out_channels), dtype=x.features.dtype, device=x.features.device)
+            out = wide[:, :self.out_channels]
         if torch.is_grad_enabled() and (x.features.requires_grad or self.weight.requires_grad):
-            if scale is not None or residual is not None or relu:
+            if scale is not None or residual is not None or relu or out is not None:
                 raise RuntimeError('the fused conv epilogue is an inference path; training runs conv, BatchNorm, ReLU separately')
             nbr_bwd, mirror = self._table_bwd(x)
             feats = _SparseConvFunction.apply(x.features, self.weight, self.bias, nbr, nbr_bwd, mirror, x.features.shape[0],
                                               self._packed)
         else:
-            feats = sparse_conv_forward(x.features, nbr, self.weight, self.bias, self._packed, scale, shift, residual, relu)
-        return out_proto(feats)
+            feats = sparse_conv_forward(x.features, nbr, self.weight, self.bias, self._packed, scale, shift, residual, relu,
+                                        out=out)
+        res = out_proto(feats)
+        if wide is not None:
+            res._os3d_wide = wide
+        return res
 
 
 class SubMConv3d(_SparseConvBase):
@@ -310,7 +329,9 @@ class SparseSequential(SparseModule):
     def __len__(self):
         return len(self._modules)
 
-    def forward(self, x):
+    def forward(self, x, wide_out=False):
+        """``wide_out`` (inference): the last fused (conv, BatchNorm[, ReLU]) group writes into the left half of a double-width
+        buffer (see _SparseConvBase.forward)."""
         mods = list(self._modules.values())
         i = 0
         while i < len(mods):
@@ -319,8 +340,9 @@ class SparseSequential(SparseModule):
                     and isinstance(mods[i + 1], nn.BatchNorm1d) and isinstance(x, SparseConvTensor):
                 relu = i + 2 < len(mods) and isinstance(mods[i + 2], nn.ReLU)
                 scale, shift = bn_scale_shift(mods[i + 1], m.bias)
-                x = m(x, scale=scale, shift=shift, relu=relu)
-                i += 3 if relu else 2
+                step = 3 if relu else 2
+                x = m(x, scale=scale, shift=shift, relu=relu, wide_out=wide_out and i + step == len(mods))
+                i += step
                 continue
             if isinstance(m, SparseModule):
                 x = m(x)
