@@ -41,3 +41,25 @@ def test_no_cpu_fallback():
     from openseg3d_b200.ops import voxel_to_point
     with pytest.raises(RuntimeError):
         voxel_to_point(torch.zeros(4, 8), torch.zeros(3, dtype=torch.long))
+
+
+def test_dense_kernel_planners_on_cpu():
+    """The host-side planners that decide which dense tcgen05 kernel takes a layer (shared-memory / tensor-memory
+    budgets) are plain C and run without a GPU: the widths of the reference model must land where DESIGN.md says."""
+    from openseg3d_b200 import _lib
+    from openseg3d_b200.ops.mlp_chain import MlpChain, SwformerMlp
+    L = _lib.lib()
+    # persistent Linear: N <= 256 with the weights resident; the level-4 width does not fit
+    assert L.os3d_linear_tc_fits(48, 48) and L.os3d_linear_tc_fits(192, 192) and L.os3d_linear_tc_fits(96, 256)
+    assert not L.os3d_linear_tc_fits(384, 384) and not L.os3d_linear_tc_fits(96, 40) and not L.os3d_linear_tc_fits(0, 64)
+    # SWFormer MLP with streamed weights: levels 1-3 (C = 48, 96, 192, hidden 2C); level 4 is out
+    assert SwformerMlp.fits(48, 96) and SwformerMlp.fits(96, 192) and SwformerMlp.fits(192, 384)
+    assert not SwformerMlp.fits(384, 768) and not SwformerMlp.fits(50, 100) and not SwformerMlp.fits(96, 200)
+    # resident-weight chains: Segformer's point MLPs (segformer.py:21-32,58-76) fit, with and without the fp32 front layer
+    assert MlpChain.fits([(128, 64), (256, 128), (64, 256)], front=True)
+    assert MlpChain.fits([(256, 96), (128, 256), (64, 128)])
+    assert MlpChain.fits([(64, 64), (22, 64)])
+    assert not MlpChain.fits([(64, 64)])                              # one layer: os3d_linear_tc_bf16
+    assert not MlpChain.fits([(512, 64), (64, 512)])                  # wider than a tensor-memory accumulator
+    assert not MlpChain.fits([(384, 192), (192, 384)])                # weights beyond shared memory
+    assert not MlpChain.fits([(128, 64), (64, 96)])                   # widths do not chain
