@@ -228,12 +228,12 @@ def main():
     conv_flops = sum(by.get(e, [0.0, 0.0, 0, 0.0])[1] for e in entries)
     conv_n = sum(by.get(e, [0.0, 0.0, 0, 0.0])[2] for e in entries)
     achieved = conv_flops / (conv_ms * 1e-3) / 1e12 if conv_ms else 0.0
-    traffic, traffic_src = None, None
+    traffic, traffic_src, traffic_all = None, None, {}
     prof_dir = os.path.join(ROOT, 'profiles')
     cands = sorted(f for f in os.listdir(prof_dir) if f.endswith('_traffic.json')) if os.path.isdir(prof_dir) else []
     if cands and dtype == torch.bfloat16:
-        t = json.load(open(os.path.join(prof_dir, cands[-1])))
-        traffic, traffic_src = t['dram_bytes_per_launch'], 'profiles/' + cands[-1]
+        traffic_all = json.load(open(os.path.join(prof_dir, cands[-1])))
+        traffic, traffic_src = traffic_all['dram_bytes_per_launch'], 'profiles/' + cands[-1]
     roofline = {'kernel': kname, 'bound': 'tensor', 'achieved': achieved, 'peak': pk['tensor'],
                 'unit': 'TFLOP/s', 'frac': achieved / pk['tensor'], 'traffic': traffic, 'traffic_unit': 'bytes/launch',
                 'traffic_source': traffic_src, 'peak_source': pk['src'] + ' (bf16_tflops_sustained: kernel timed inside a long step)',
@@ -260,6 +260,9 @@ def main():
             'achieved_tflops': round(at[1] / (at[0] * 1e-3) / 1e12, 1),
             'frac_of_tensor_peak': round(at[1] / (at[0] * 1e-3) / 1e12 / pk['tensor'], 4),
             'note': 'instruction bound in the softmax (ncu: profiles/r01c_attention_l2_full.txt), not by the tensor pipe'}
+        tk = traffic_all.get('window_attention_tc_kernel')
+        if isinstance(tk, dict) and tk.get('dram_bytes_per_step'):
+            roofline['window_attention_tc_kernel']['dram_mb_per_step_ncu'] = round(tk['dram_bytes_per_step'] / 1e6, 1)
     # the persistent dense kernels of the SWFormer layers and the point MLPs (linear_tc_kernel: out-proj + residual +
     # LayerNorm, level-4 fc2; swformer_mlp_tc_kernel: fc1 + GELU + fc2 + LayerNorm + residual with the hidden tensor on
     # chip; mlp_chain_tc_kernel: the BatchNorm-folded point MLPs).  Their tensor work is small next to their activations,
@@ -273,6 +276,9 @@ def main():
                 'achieved_gbs': round(lt[3] / (lt[0] * 1e-3) / 1e9, 1),
                 'frac_of_hbm_peak': round(lt[3] / (lt[0] * 1e-3) / 1e9 / pk['hbm'], 3),
                 'achieved_tflops': round(lt[1] / (lt[0] * 1e-3) / 1e12, 1)}
+            tk = traffic_all.get(key)                 # measured DRAM bytes (ncu launch list) next to the algorithmic ones
+            if isinstance(tk, dict) and tk.get('dram_bytes_per_step'):
+                roofline[key]['dram_mb_per_step_ncu'] = round(tk['dram_bytes_per_step'] / 1e6, 1)
 
     line = {'metric': 'points/sec, Waymo 1-sweep seg forward', 'value': value, 'unit': 'points/s', 'n_gpus': world,
             'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': total_ms / args.steps, 'higher_is_better': True,
