@@ -108,7 +108,9 @@ def run_reference(args):
     line = {'impl': 'reference', 'metric': 'points/sec, Waymo 1-sweep seg forward', 'value': pps, 'unit': 'points/s',
             'n_gpus': args.gpus, 'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': ms, 'higher_is_better': True,
             'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
-            'config': {'workload': f'{CONFIG} forward, oracle CPU port, {sample}'},
+            'config': {'workload': f'configs/{CONFIG}.yaml inference, voxelize + sparse UNet + window attention, random-init '
+                                   '(the GPU arm\'s model and synthetic frames; oracle CPU port, bounded sample per step)',
+                       'sample': sample, 'parallelism': f'{cores} host threads'},
             'cpu_baseline': {'value': pps, 'unit': 'points/s', 'cores': cores, 'kind': 'port', 'sample': sample},
             'e2e': {'value': pps, 'unit': 'points/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
             'gpu_launches': 0}
