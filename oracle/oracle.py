@@ -13,7 +13,10 @@ Pinning status (DESIGN.md "Oracle"):
                            -- PINNED against the reference's own modules imported in the build container
                               (tests/golden/swformer_*.npz), with get_inner_win_inds replaced by the stable rank.
   * voxel_to_point         -- PINNED (reference op is pure torch; golden in tests/golden/stage1_*.npz).
-  * scatter mean/max       -- torch_scatter absent => restated from its documented semantics; PARITY UNPINNED.
+  * voxel_avg_pooling      -- PINNED against the reference's own CPU function voxel_pooling_forward_cpu, compiled from
+                              /root/reference into oracle/_ref/ by oracle/build_ref.py (tests/golden/voxel_avg_pooling.npz).
+  * scatter mean/max (VFE) -- torch_scatter absent => restated from its documented semantics; PARITY UNPINNED
+                              (the mean is cross-checked against the pinned avg pooling).
   * kernel maps, sparse conv -- spconv absent => PARITY UNPINNED against spconv; pinned against torch dense
                               conv3d / conv_transpose3d instead (tests/test_oracle_spconv.py).
 """

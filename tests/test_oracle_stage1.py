@@ -65,6 +65,37 @@ def test_scatter_semantics():
                           torch.tensor([[7., 8.], [-2., -4.]]))
 
 
+@pytest.mark.parametrize('name', ['small', 'ragged', 'heavy'])
+def test_voxel_avg_pooling_matches_reference_cpu_function(golden_dir, name):
+    """oracle.voxel_avg_pooling against the output of the reference's own voxel_pooling_forward_cpu
+    (seg3d/ops/voxel_pooling/src/voxel_pooling.cpp:5-23, compiled from /root/reference by oracle/build_ref.py;
+    vectors made by tests/golden/make_golden_pooling.py): ids outside [0, M) skipped, an empty voxel, a voxel holding
+    80 % of the points.  Same divide-then-accumulate order -> bit-exact."""
+    g = np.load(os.path.join(golden_dir, 'voxel_avg_pooling.npz'))
+    out = oracle.voxel_avg_pooling(torch.from_numpy(g[f'{name}_feats']), torch.from_numpy(g[f'{name}_ids']),
+                                   torch.from_numpy(g[f'{name}_counts']))
+    assert torch.equal(out, torch.from_numpy(g[f'{name}_out']))
+    # the mean reduction of VFE (scatter 'mean', vfe.py:24-25) is the same quantity up to summation order
+    ids = torch.from_numpy(g[f'{name}_ids']).long()
+    ids = torch.where((ids >= 0) & (ids < g[f'{name}_counts'].shape[0]), ids, torch.full_like(ids, -1))
+    mean = oracle.scatter_reduce(torch.from_numpy(g[f'{name}_feats']), ids, 'mean')
+    assert torch.allclose(mean[:out.shape[0]], out[:mean.shape[0]], rtol=1e-5, atol=1e-5)
+
+
+def test_voxel_avg_pooling_against_live_reference_build():
+    """Where the reference sources exist (the build container), the compiled reference function itself is the checker."""
+    from oracle import build_ref
+    if not os.path.exists(build_ref.REF_SRC) and not os.path.exists(build_ref.out_path()):
+        pytest.skip('no /root/reference and no prebuilt oracle/_ref here')
+    ext = build_ref.load()
+    g = torch.Generator().manual_seed(3)
+    feats = torch.randn(777, 24, generator=g)
+    ids = torch.randint(-1, 41, (777,), generator=g, dtype=torch.int32)
+    counts = torch.bincount(ids[(ids >= 0) & (ids < 40)].long(), minlength=40).int()
+    ref = ext.voxel_pooling_forward_cpu(feats, ids, counts)
+    assert torch.equal(oracle.voxel_avg_pooling(feats, ids, counts), ref)
+
+
 def test_folded_point_mlp_equals_sequential():
     """Inference-time BatchNorm folding of the point-wise MLPs (segformer.py:21-32,58-76) is exact up to fp32
     rounding: same nn.Sequential, same state_dict, evaluated both ways on CPU."""
