@@ -94,6 +94,11 @@ def test_voxel_avg_pooling_against_live_reference_build():
     counts = torch.bincount(ids[(ids >= 0) & (ids < 40)].long(), minlength=40).int()
     ref = ext.voxel_pooling_forward_cpu(feats, ids, counts)
     assert torch.equal(oracle.voxel_avg_pooling(feats, ids, counts), ref)
+    # backward (voxel_pooling.cpp:25-43): autograd of the restatement == the reference's hand-written CPU backward
+    x = feats.clone().requires_grad_()
+    top = torch.randn(ref.shape, generator=g)
+    oracle.voxel_avg_pooling(x, ids, counts).backward(top)
+    assert torch.equal(x.grad, ext.voxel_pooling_backward_cpu(top, ids, counts, feats.shape[0]))
 
 
 def test_folded_point_mlp_equals_sequential():
