@@ -53,8 +53,14 @@ __device__ __forceinline__ uint32_t core_off(int r, int c, int sbo) { return (r 
 // DP: padded head dim.  KB: keys per block.  TMEM: S in columns [0, KB), O in [KB, KB + DP) of a power-of-two allocation
 // -- with KB = 32 and DP = 16 that is 64 columns, so 8 CTAs share an SM (and short windows waste half as many masked
 // score columns); KB = 64 otherwise (128 columns, 4 CTAs).
-template <int DP, int KB>
-__global__ void __launch_bounds__(kThreads, KB == 32 ? 8 : (DP <= 32 ? 4 : 3)) window_attention_tc_kernel(const Params p) {
+//
+// ISSUER = 1 (experimental, OS3D_ATTN_ISSUER=1; not the default until it has been measured on a GPU): a fifth warp does
+// nothing but issue the MMAs.  The four softmax warps then never execute a block-wide barrier in the key loop -- they
+// publish K / V (k_ready) and P (p_ready) with an mbarrier arrive and go on -- and warp 0 is no longer the straggler that
+// issues `UTCHMMA`s while the other three wait for it (ncu, ISSUER = 0: 24 % of the stall samples on those two barriers).
+template <int DP, int KB, int ISSUER = 0>
+__global__ void __launch_bounds__(kThreads + 32 * ISSUER, KB == 32 ? (ISSUER ? 6 : 8) : (DP <= 32 ? 4 : 3))
+    window_attention_tc_kernel(const Params p) {
   constexpr int kBlockKeys = KB;
   constexpr int kTmemCols = (KB + DP) <= 64 ? 64 : 128;
   constexpr int kChunks = DP / 8;                         // 16-byte chunks per head slice
@@ -70,10 +76,10 @@ __global__ void __launch_bounds__(kThreads, KB == 32 ? 8 : (DP <= 32 ? 4 : 3)) w
   __shared__ __align__(128) uint8_t k_s[kKBytes];
   __shared__ __align__(128) uint8_t v_s[kVBytes];
   __shared__ __align__(128) uint8_t p_s[kPBytes];
-  __shared__ __align__(8) uint64_t bars[2];
+  __shared__ __align__(8) uint64_t bars[4];               // MMA 1 done, MMA 2 done, (ISSUER) k_ready, p_ready
   __shared__ uint32_t tmem_slot;
 
-  const int tid = threadIdx.x, warp = tid >> 5;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   // heads of one query tile are adjacent in launch order: they run at the same time and share the q / k / v rows (each
   // head reads a 32-96 byte slice of the same lines) while those are still in L2.  With heads on the slow grid axis
   // every line came from HBM once per head (ncu: 3.1 GB of DRAM reads per launch for 0.7 GB of q / k / v).
@@ -84,16 +90,20 @@ __global__ void __launch_bounds__(kThreads, KB == 32 ? 8 : (DP <= 32 ? 4 : 3)) w
   const int p_last = min(p0 + kTileQ, n_tok) - 1;
 
   const uint32_t bar1 = smem_u32(&bars[0]), bar2 = smem_u32(&bars[1]);
+  const uint32_t k_ready = smem_u32(&bars[2]), p_ready = smem_u32(&bars[3]);
   if (tid == 0) {
     mbar_init(bar1, 1);
     mbar_init(bar2, 1);
+    mbar_init(k_ready, 4);
+    mbar_init(p_ready, 4);
     fence_barrier_init();
   }
   if (warp == 0) tmem_alloc(smem_u32(&tmem_slot), kTmemCols);
 
   // ---- this thread's query row ----
+  const bool issuer = ISSUER && warp == 4;               // (warp-uniform) this warp only issues MMAs
   const int qp = p0 + tid;
-  const bool q_ok = qp <= p_last;
+  const bool q_ok = !issuer && qp <= p_last;
   int qws = 0, qlen = 0;                 // this row's window = grouped positions [qws, qws + qlen)
   int32_t qrow = 0;
   if (q_ok) {
@@ -102,7 +112,7 @@ __global__ void __launch_bounds__(kThreads, KB == 32 ? 8 : (DP <= 32 ? 4 : 3)) w
     qlen = seg.y;
     qrow = __ldg(p.order + qp);
   }
-  {
+  if (!issuer) {
     float f[DP];
     if (q_ok) {
       const uint4 *src = reinterpret_cast<const uint4 *>(p.q + (int64_t)qrow * p.ld + h * DP);
@@ -153,6 +163,32 @@ __global__ void __launch_bounds__(kThreads, KB == 32 ? 8 : (DP <= 32 ? 4 : 3)) w
   const float scale = 1.4426950408889634f / fmaxf(__ldg(p.tau), p.tau_min);
   const bool fixed_max = scale <= 60.0f;
 
+  if (issuer) {
+    // ---- MMA issuer warp (ISSUER = 1): S = Q K^T when the four softmax warps have published K / V, O += P V when they
+    // have published P; descriptors are built once
+    const uint64_t qd = make_kmajor_nosw_desc(smem_u32(q_s), kLbo, kSboQ), kd = make_kmajor_nosw_desc(smem_u32(k_s), kLbo, kSboQ);
+    const uint64_t pd = make_kmajor_nosw_desc(smem_u32(p_s), kLbo, kSboP), vd = make_kmajor_nosw_desc(smem_u32(v_s), kLbo, kSboV);
+    constexpr uint64_t kStep = (uint64_t)(2 * kLbo) >> 4;       // one K = 16 step along the operand, in descriptor units
+    for (int blk = 0; blk < n_blocks; ++blk) {
+      mbar_wait(k_ready, (uint32_t)blk & 1u);
+      tc_fence_after();
+      if (elect_one()) {
+#pragma unroll
+        for (int s = 0; s < DP / 16; ++s) umma_bf16(tmem_base, qd + s * kStep, kd + s * kStep, idesc1, s > 0 ? 1u : 0u);
+        umma_commit(bar1);
+      }
+      __syncwarp();
+      mbar_wait(p_ready, (uint32_t)blk & 1u);
+      tc_fence_after();
+      if (elect_one()) {
+#pragma unroll
+        for (int s2 = 0; s2 < kBlockKeys / 16; ++s2)
+          umma_bf16(tmem_base + kBlockKeys, pd + s2 * kStep, vd + s2 * kStep, idesc2, (blk > 0 || s2 > 0) ? 1u : 0u);
+        umma_commit(bar2);
+      }
+      __syncwarp();
+    }
+  } else {
   float m_run = -INFINITY, l_run = 0.0f;
   uint32_t ph1 = 0, ph2 = 0;
 
@@ -229,6 +265,10 @@ __global__ void __launch_bounds__(kThreads, KB == 32 ? 8 : (DP <= 32 ? 4 : 3)) w
     }
     fence_proxy_async();
     tc_fence_before();
+    if constexpr (ISSUER) {
+      __syncwarp();
+      if (lane == 0) mbar_arrive(k_ready);
+    } else {
     __syncthreads();
     if (tid == 0) {
       tc_fence_after();
@@ -237,6 +277,7 @@ __global__ void __launch_bounds__(kThreads, KB == 32 ? 8 : (DP <= 32 ? 4 : 3)) w
         umma_bf16(tmem_base, make_kmajor_nosw_desc(smem_u32(q_s) + s * 2 * kLbo, kLbo, kSboQ),
                   make_kmajor_nosw_desc(smem_u32(k_s) + s * 2 * kLbo, kLbo, kSboQ), idesc1, s > 0 ? 1u : 0u);
       umma_commit(bar1);
+    }
     }
     prefetch(blk + 1);        // global loads for the next key block fly during MMA 1, the softmax and MMA 2
     mbar_wait(bar1, ph1);
@@ -330,6 +371,10 @@ __global__ void __launch_bounds__(kThreads, KB == 32 ? 8 : (DP <= 32 ? 4 : 3)) w
     }
     fence_proxy_async();
     tc_fence_before();
+    if constexpr (ISSUER) {
+      __syncwarp();
+      if (lane == 0) mbar_arrive(p_ready);
+    } else {
     __syncthreads();
     if (tid == 0) {
       tc_fence_after();
@@ -338,6 +383,7 @@ __global__ void __launch_bounds__(kThreads, KB == 32 ? 8 : (DP <= 32 ? 4 : 3)) w
         umma_bf16(tmem_base + kBlockKeys, make_kmajor_nosw_desc(smem_u32(p_s) + s2 * 2 * kLbo, kLbo, kSboP),
                   make_kmajor_nosw_desc(smem_u32(v_s) + s2 * 2 * kLbo, kLbo, kSboV), idesc2, (blk > 0 || s2 > 0) ? 1u : 0u);
       umma_commit(bar2);
+    }
     }
   }
 
@@ -364,6 +410,7 @@ __global__ void __launch_bounds__(kThreads, KB == 32 ? 8 : (DP <= 32 ? 4 : 3)) w
       }
     }
   }
+  }   // !issuer
   tc_fence_before();
   __syncthreads();
   if (warp == 0) {
@@ -399,6 +446,15 @@ extern "C" int os3d_window_attention_bf16_tc(const void *q, const void *k, const
   cudaStream_t st = (cudaStream_t)stream;
   const char *e = getenv("OS3D_ATTN_KB");                       // tuning override: keys per block for dp = 16
   const bool kb32 = e ? atoi(e) != 64 : true;
+  const char *ei = getenv("OS3D_ATTN_ISSUER");                  // experimental variant with a dedicated MMA-issuing warp
+  if (ei && atoi(ei) == 1) {
+    const int th = attn_tc::kThreads + 32;
+    if (dp == 16) attn_tc::window_attention_tc_kernel<16, 32, 1><<<grid, th, 0, st>>>(p);
+    else if (dp == 32) attn_tc::window_attention_tc_kernel<32, 64, 1><<<grid, th, 0, st>>>(p);
+    else attn_tc::window_attention_tc_kernel<48, 64, 1><<<grid, th, 0, st>>>(p);
+    OS3D_LAUNCH_CHECK();
+    return 0;
+  }
   if (dp == 16 && kb32) attn_tc::window_attention_tc_kernel<16, 32><<<grid, attn_tc::kThreads, 0, st>>>(p);
   else if (dp == 16) attn_tc::window_attention_tc_kernel<16, 64><<<grid, attn_tc::kThreads, 0, st>>>(p);
   else if (dp == 32) attn_tc::window_attention_tc_kernel<32, 64><<<grid, attn_tc::kThreads, 0, st>>>(p);
