@@ -129,8 +129,10 @@ int os3d_kernel_map_order(const int32_t *nbr, int64_t m, uint32_t *keys, uint32_
  * kernel map and shared by every conv that uses the map. */
 int os3d_kernel_map_tiles(const int32_t *nbr, int64_t m, const int32_t *perm, int32_t *nbr_t, uint32_t *tile_mask,
                           void *stream);
-/* bf16 in / bf16 out, f32 accumulate in TMEM on the tcgen05 tensor cores; the gathered operand is fetched by TMA
- * (cp.async.bulk.tensor tile::gather4) straight into the UMMA shared-memory layout.  Fused epilogue:
+/* bf16 in / bf16 out, f32 accumulate in TMEM on the tcgen05 tensor cores; the gathered operand rows are fetched by
+ * 16-byte cp.async (LDGSTS, zero-fill for absent neighbours) straight into the SWIZZLE_128B UMMA shared-memory layout,
+ * the weight K-blocks by cp.async.bulk (TMA tile::gather4 was built, measured 1.0-4.3x slower and dropped: DESIGN.md
+ * section 3.1).  Fused epilogue:
  * y = acc*scale[c]+shift[c] (bias and folded BatchNorm), optional residual add [m_out, cout] bf16, optional ReLU.
  * scale/shift (both or neither) and residual may be NULL.  flags: bit 0 = ReLU; bit 1 = the residual has 2*cout
  * channels per row and residual[r, 2c] + residual[r, 2c+1] is added AFTER the ReLU (UpBlock's

@@ -135,9 +135,10 @@ PROFILE = None      # bench.py sets this to a list to collect (name, start_event
 class Work(float):
     """Algorithmic FLOPs of a call that also carries its algorithmic HBM bytes (``.bytes``) for the bench's roofline table."""
 
-    def __new__(cls, flops, nbytes=0.0):
+    def __new__(cls, flops, nbytes=0.0, detail=None):
         w = super().__new__(cls, flops)
         w.bytes = float(nbytes)
+        w.detail = detail            # e.g. dict(cin=, cout=, m_out=, pairs=) of a sparse conv: bench.py's per-layer table
         return w
 
 

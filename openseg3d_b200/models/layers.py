@@ -95,6 +95,56 @@ def window2flat(feat_3d_dict, inds):
     return out
 
 
+class KeyMaskDict(dict):
+    """``key_mask_shift{i}``: {level: [R, T] bool, True on padded slots} as get_key_padding_mask builds it
+    (point_transformer_layer.py:210-220).  The hot path never pads, so the masks are materialised on first access
+    (one host sync per level, like the reference)."""
+
+    def __init__(self, inds):
+        super().__init__()
+        self._inds, self._done = inds, False
+
+    def _ensure(self):
+        if not self._done:
+            self._done = True
+            inds = self._inds
+            if not inds.levels():
+                inds.materialize()
+            binfo = inds['batching_info']
+            dev = inds['segments'].level.device
+            for bl, (slot, where) in inds.levels().items():
+                t = binfo[bl]['max_tokens']
+                r = int(torch.div(slot, t, rounding_mode='floor').max().item()) + 1
+                mask = torch.ones(r * t, dtype=torch.bool, device=dev)
+                mask[slot] = False
+                super().__setitem__(bl, mask.reshape(r, t))
+        return self
+
+    def __getitem__(self, k):
+        return dict.__getitem__(self._ensure(), k)
+
+    def __contains__(self, k):
+        return dict.__contains__(self._ensure(), k)
+
+    def __iter__(self):
+        return dict.__iter__(self._ensure())
+
+    def __len__(self):
+        return dict.__len__(self._ensure())
+
+    def keys(self):
+        return dict.keys(self._ensure())
+
+    def items(self):
+        return dict.items(self._ensure())
+
+    def values(self):
+        return dict.values(self._ensure())
+
+    def get(self, k, default=None):
+        return dict.get(self._ensure(), k, default)
+
+
 class PosDict(dict):
     """``pos_dict_shift{i}``.  'flat' ([M, C] sinusoidal embedding, point_transformer_layer.py:152-207) is computed on
     first access: the bf16 hot path never needs it, because (x + pos) W^T = x W^T + pos W^T and pos takes only
@@ -159,6 +209,22 @@ class SparseWindowPartitionLayer(nn.Module):
         self.normalize_pos = normalize_pos
         self.pos_temperature = pos_temperature
         self._tables = {}
+        self._may_drop = self._can_drop(batching_info, window_shape)
+
+    @staticmethod
+    def _can_drop(batching_info, window_shape):
+        """True when some window occupancy 1..volume falls outside every batching range or above its level's max_tokens
+        (batching_single_shift's keep_mask, point_transformer_layer.py:71-87).  False for the reference's configs."""
+        volume = 1
+        for w in window_shape:
+            volume *= int(w)
+        ok = [False] * (volume + 1)
+        for info in batching_info.values():
+            lo, hi = [int(v) for v in info['batching_range']]
+            for n in range(max(lo, 1), min(hi, volume + 1)):
+                if n <= int(info['max_tokens']):
+                    ok[n] = True
+        return not all(ok[1:])
 
     @torch.no_grad()
     def pos_table(self, feat_dim, device):
@@ -243,7 +309,12 @@ class SparseWindowPartitionLayer(nn.Module):
             info[f'flat2win_inds_shift{i}'] = Flat2WinInds(segments=seg, voxel_batching_level=seg.level,
                                                            batching_info=self.batching_info)
             info[f'pos_dict_shift{i}'] = PosDict(self, seg, feats.shape[1], feats.dtype)
-            info[f'key_mask_shift{i}'] = {}     # padding masks are implicit in the segment lengths
+            info[f'key_mask_shift{i}'] = KeyMaskDict(info[f'flat2win_inds_shift{i}'])    # materialised on first access
+            if self._may_drop:
+                # a batching_info that can leave tokens without a level or over a level's capacity: the reference drops
+                # them and then desynchronises features and indices -- fail loudly instead of
+                # returning rows no kernel writes.  One host read per partition, only for such configurations.
+                seg.check_no_drop()
         return info
 
 
@@ -299,7 +370,8 @@ class CosineMultiheadAttention(nn.MultiheadAttention):
         """(in_proj_weight, in_proj_bias, out_proj.weight, out_proj.bias) in the compute dtype, cached."""
         if dtype == self.in_proj_weight.dtype:
             return self.in_proj_weight, self.in_proj_bias, self.out_proj.weight, self.out_proj.bias
-        tag = (dtype, self.in_proj_weight._version, self.out_proj.weight._version, self.in_proj_weight.data_ptr())
+        tag = (dtype, self.in_proj_weight._version, self.in_proj_bias._version, self.out_proj.weight._version,
+               self.out_proj.bias._version, self.in_proj_weight.data_ptr())
         if self._cast.get('tag') != tag:
             self._cast = {'tag': tag, 'p': tuple(p.detach().to(dtype) for p in (
                 self.in_proj_weight, self.in_proj_bias, self.out_proj.weight, self.out_proj.bias))}
@@ -309,7 +381,8 @@ class CosineMultiheadAttention(nn.MultiheadAttention):
         """Projection weights with every head's d channels padded to dp = ceil(d / 16) * 16 (zero rows / columns), the
         layout os3d_window_attention_bf16_tc consumes: (w_qk [2*H*dp, C], b_qk, w_v [H*dp, C], b_v, w_out [C, H*dp],
         b_out, dp).  Zero padding changes neither dot products nor norms."""
-        tag = (dtype, self.in_proj_weight._version, self.out_proj.weight._version, self.in_proj_weight.data_ptr())
+        tag = (dtype, self.in_proj_weight._version, self.in_proj_bias._version, self.out_proj.weight._version,
+               self.out_proj.bias._version, self.in_proj_weight.data_ptr())
         if self._cast.get('pad_tag') != tag:
             c, h = self.embed_dim, self.num_heads
             d = c // h
@@ -335,7 +408,7 @@ class CosineMultiheadAttention(nn.MultiheadAttention):
 
     def _out_proj_chunks(self):
         """Head-padded output projection [C, H*dp] as a tensor-core image (PackedLinearCache chunks)."""
-        tag = (self.out_proj.weight._version, self.out_proj.weight.data_ptr())
+        tag = (self.out_proj.weight._version, self.out_proj.bias._version, self.out_proj.weight.data_ptr())
         hit = self.__dict__.get('_o_chunks')
         if hit is None or hit[0] != tag:
             _, _, _, _, w_o, b_o, _ = self.params_head_padded(torch.float32)
@@ -359,6 +432,60 @@ class CosineMultiheadAttention(nn.MultiheadAttention):
                   seg.order, seg.pos_seg, seg.level_info, self.tau.detach().float().reshape(1), float(self.tau_min),
                   out, hd, work=lambda: 4.0 * seg.sum_sq_tokens() * self.embed_dim)
         return out, o_c
+
+    def forward(self, query, key, value, key_padding_mask=None, need_weights=True, attn_mask=None):
+        """The reference signature (cosine_msa.py:433-501) on padded windows: query / key / value [T, R, C] (sequence
+        first), key_padding_mask [R, T] bool (True = padding).  Runs the COSINE attention of this class -- never the
+        dot-product forward nn.MultiheadAttention would inherit -- by viewing every window's valid slots as one segment of
+        the flat row list [T * R, C] and calling the same variable-length kernels as forward_segments().  Rows of padded
+        slots come back as out_proj.bias (their attention output is zero).  Returns (out [T, R, C], weights): weights
+        are the head-averaged probabilities [R, T, T] when need_weights (computed with plain torch ops; the
+        reference's callers discard them, point_transformer_layer.py:253) else None."""
+        if attn_mask is not None:
+            raise NotImplementedError('attn_mask is never used by the reference model')
+        if query.dim() != 3 or key.shape != query.shape or value.shape != query.shape:
+            raise RuntimeError('CosineMultiheadAttention.forward expects query / key / value of shape [T, R, C]')
+        if torch.is_grad_enabled() and (query.requires_grad or self.in_proj_weight.requires_grad):
+            raise NotImplementedError('padded-window forward is an inference entry point; training goes through '
+                                      'WindowAttention / forward_segments')
+        _lib.require_cuda(query, key, value)
+        t, r, c = query.shape
+        h = self.num_heads
+        dev = query.device
+        valid = torch.ones((r, t), dtype=torch.bool, device=dev) if key_padding_mask is None else ~key_padding_mask.bool()
+        w_in, b_in, w_out, b_out = self.params(query.dtype)
+        q = F.linear(query.reshape(t * r, c), w_in[:c], b_in[:c])
+        k = F.linear(key.reshape(t * r, c), w_in[c:2 * c], b_in[c:2 * c])
+        v = F.linear(value.reshape(t * r, c), w_in[2 * c:], b_in[2 * c:]).contiguous()
+        qk = torch.cat([q, k], dim=1).contiguous()                   # [T*R, 2C]: q | k, as forward_segments lays them out
+        # segments: window r' = the valid slots of row r' of the mask, in slot order; flat row of slot (r', t') = t' * R + r'
+        seg_len_all = valid.sum(dim=1).int()
+        nz = seg_len_all > 0
+        rt = torch.nonzero(valid)                                    # sorted by (window, slot)
+        order = (rt[:, 1] * r + rt[:, 0]).int().contiguous()
+        seg_len = seg_len_all[nz].contiguous()
+        seg_start = (torch.cumsum(seg_len, 0) - seg_len).int().contiguous()
+        n_win, n_tok = int(seg_len.shape[0]), int(order.shape[0])
+        level_info = torch.zeros(16, dtype=torch.int32, device=dev)
+        level_info[0], level_info[13], level_info[14] = n_win, n_win, n_tok
+        es = query.element_size()
+        k_ptr = _lib._Raw(qk.data_ptr() + c * es)
+        _lib.call('os3d_qk_normalize', qk, k_ptr, 2 * c, t * r, c, h, es)
+        out = torch.zeros((t * r, c), dtype=query.dtype, device=dev)
+        if n_tok:
+            lvl_tokens = (ctypes.c_int * 4)(t, 0, 0, 0)
+            _lib.call('os3d_window_attention', qk, k_ptr, v, 2 * c, c, t * r, c, h, order, seg_start, seg_len, level_info,
+                      ctypes.byref(lvl_tokens), self.tau.detach().float().reshape(1), float(self.tau_min), 0.0, 0, es, out)
+        res = F.linear(out, w_out, b_out).reshape(t, r, c)
+        weights = None
+        if need_weights:
+            d = c // h
+            qn = qk[:, :c].reshape(t, r, h, d).permute(1, 2, 0, 3).float()           # [R, h, T, d] (already normalised)
+            kn = qk[:, c:].reshape(t, r, h, d).permute(1, 2, 0, 3).float()
+            s_ = qn @ kn.transpose(-2, -1) / self.tau.detach().float().reshape(()).clamp(min=self.tau_min)
+            s_ = s_.masked_fill(~valid[:, None, None, :], float('-inf'))
+            weights = s_.softmax(dim=-1).mean(dim=1).to(query.dtype)
+        return res, weights
 
     def tensor_core_ok(self, feat):
         return feat.dtype == torch.bfloat16 and self.embed_dim // self.num_heads <= 48 and self.embed_dim % 8 == 0

@@ -44,7 +44,7 @@ def sparse_conv_forward(features, nbr, weight, bias, packed_cache, scale=None, s
         w = packed_cache.get('f32', weight)
         out = torch.empty((m_out, cout), dtype=torch.float32, device=features.device)
         _lib.call('os3d_spconv_fwd_f32', features, nbr, m_out, cin, cout, w, bias if scale is None else None, out,
-                  work=lambda: 2.0 * cin * cout * int((nbr >= 0).sum().item()))
+                  work=lambda: _conv_work(nbr, features.shape[0], cin, cout, 4, residual))
         if scale is not None:
             out = out * scale + shift
         flags = int(relu)
@@ -70,9 +70,23 @@ def sparse_conv_forward(features, nbr, weight, bias, packed_cache, scale=None, s
         nbr_t, tile_mask, perm = kernel_map_tiles(nbr)
         _lib.call('os3d_spconv_fwd_bf16_ld', features, features.shape[0], nbr_t, tile_mask, perm, m_out, cin_pad, cout, w,
                   scale, shift, residual.contiguous() if residual is not None else None, int(relu),
-                  _lib._Raw(out.data_ptr()), out.stride(0), work=lambda: 2.0 * cin * cout * int((nbr >= 0).sum().item()))
+                  _lib._Raw(out.data_ptr()), out.stride(0),
+                  work=lambda: _conv_work(nbr, features.shape[0], cin, cout, 2, residual))
         return out
     raise RuntimeError(f'sparse conv: unsupported feature dtype {features.dtype}')
+
+
+def _conv_work(nbr, m_in, cin, cout, es, residual):
+    """Algorithmic work of one sparse conv (profiling only; one host read, cached on the map): FLOPs = 2 * pairs * Cin *
+    Cout; bytes = input rows + output rows (+ residual rows) + the 27 map entries of every output row."""
+    pairs = getattr(nbr, '_os3d_pairs', None)
+    if pairs is None:
+        pairs = nbr._os3d_pairs = int((nbr >= 0).sum().item())
+    m_out = nbr.shape[0]
+    nbytes = es * (m_in * cin + m_out * cout) + 27 * 4 * m_out
+    if residual is not None:
+        nbytes += residual.numel() * residual.element_size()
+    return _lib.Work(2.0 * cin * cout * pairs, nbytes, dict(cin=cin, cout=cout, m_out=m_out, pairs=pairs))
 
 
 def kernel_map_tiles(nbr):
@@ -93,7 +107,8 @@ def kernel_map_tiles(nbr):
             nbytes = ctypes.c_int64(0)
             _lib.lib().os3d_kernel_map_order_scratch(m, ctypes.byref(nbytes))
             temp = torch.empty(max(nbytes.value, 1), dtype=torch.uint8, device=nbr.device)
-            _lib.call('os3d_kernel_map_order', nbr, m, scratch[0], scratch[1], scratch[2], perm, temp, nbytes.value)
+            _lib.call('os3d_kernel_map_order', nbr, m, scratch[0], scratch[1], scratch[2], perm, temp, nbytes.value,
+                      work=lambda: m * 27 * 4 + m * 4 * 4)     # map read once; keys / row ids / perm written
         _lib.call('os3d_kernel_map_tiles', nbr, m, perm, nbr_t, tile_mask, work=lambda: 2 * m * 27 * 4 + m * 4)
         hit = nbr._os3d_tiles = (nbr_t, tile_mask, perm)
     return hit

@@ -468,6 +468,8 @@ def backbone_forward(sd, voxel_features, voxel_coords, sparse_shape_zyx, batchin
     y3 = _up_block(y4, x3, subm[2], inv[1], sd, 'up3.')
     y2 = _up_block(y3, x2, subm[1], inv[0], sd, 'up2.')
     y1 = _up_block(y2, x1, subm[0], subm[0], sd, 'up1.')
+    if stats is not None:            # per-stage features for the parity error tables (tests/test_gpu_full_frame.py)
+        stats['stages'] = dict(enc1=x1, enc2=x2, enc3=x3, enc4=x4, up4=y4, up3=y3, up2=y2, up1=y1)
     return dict(voxel_features=y1, voxel_out=F.linear(y1, sd['voxel_classifier.0.weight']), aux_voxel_out=aux,
                 aux_voxel_coords=idx[3], voxel_coords=idx[0])
 

@@ -258,3 +258,62 @@ def test_full_size_conv_is_independent_of_tile_order(monkeypatch):
             t = t.long() & 0x7ffffff
             return sum(((t >> b) & 1) for b in range(27)).float().mean().item()
         assert offsets_per_tile(sorted_offsets) < offsets_per_tile(storage_offsets)
+
+
+@pytest.mark.parametrize('cout', [48, 96, 192])
+def test_spconv_bf16_pair_sum_epilogue_and_pitched_output_match_oracle(cout):
+    """UpBlock's bottleneck at inference (pointtransformer.py:105-110): conv over cat([x_bottom, x_trans]) (2C channels) +
+    BatchNorm + ReLU, then `x_m + channel_reduction(cat)` -- flags = 3: the residual has 2*cout channels and
+    residual[:, 2c] + residual[:, 2c+1] is added AFTER the ReLU -- written through os3d_spconv_fwd_bf16_ld into the LEFT
+    half of a double-width buffer (output row pitch 2*cout), against the oracle's restatement of the same lines."""
+    from openseg3d_b200 import spconv
+    from openseg3d_b200.spconv.modules import sparse_conv_forward, _PackedWeights
+    from oracle import oracle
+    rng = np.random.default_rng(cout)
+    torch.manual_seed(cout)
+    shape = (12, 40, 40)
+    idx = _sites(rng, 2, shape, 3000)
+    m, cin = idx.shape[0], 2 * cout
+    cat = torch.randn(m, cin).bfloat16()
+    w = (torch.randn(cout, 3, 3, 3, cin) / np.sqrt(27 * cin) * 3).bfloat16().float()
+    scale, shift = torch.rand(cout) + 0.5, torch.randn(cout)
+    rb = spconv.build_subm_rulebook(_tensor(idx, shape, 2, cat))
+    wide = torch.full((m, 2 * cout), 7.0, dtype=torch.bfloat16, device='cuda')         # right half must stay untouched
+    y = sparse_conv_forward(cat.cuda(), rb.nbr, w.cuda(), None, _PackedWeights(), scale.cuda(), shift.cuda(), cat.cuda(), 3,
+                            out=wide[:, :cout])
+    assert y.data_ptr() == wide.data_ptr() and y.stride(0) == 2 * cout
+    assert bool((wide[:, cout:] == 7.0).all())
+    nbr, _ = oracle.subm_map(idx, shape)
+    x_m = (oracle.sparse_conv(cat.double(), nbr, w.double()) * scale.double() + shift.double()).clamp(min=0)
+    ref = x_m + cat.double().view(m, cout, 2).sum(dim=2)                              # channel_reduction :89-103
+    got = wide[:, :cout].float().cpu().double()
+    err = (got - ref).abs().max().item() / ref.abs().max().item()
+    mean_err = (got - ref).abs().mean().item() / ref.abs().mean().item()
+    assert err < 2e-2 and mean_err < 4e-3, (err, mean_err)
+
+
+def test_full_size_conv_matches_oracle():
+    """BASELINE size, ONE full frame (116k voxels at level 1, 130k at level 2): the tensor-core conv on the level-1
+    submanifold map, the strided map and its inverse against the oracle's sparse_conv (C restatement) on the same maps."""
+    from openseg3d_b200 import spconv, synthetic
+    from openseg3d_b200.core import voxelize_batch
+    from openseg3d_b200.spconv.modules import sparse_conv_forward, _PackedWeights
+    from oracle import oracle
+    pts, _ = synthetic.make_batch([0], 1, False)
+    coors, _ = voxelize_batch(torch.from_numpy(pts).cuda(), [0.1, 0.1, 0.1], [-72, -72, -2, 72, 72, 4.4])
+    x = spconv.SparseConvTensor(torch.zeros(coors.shape[0], 1, device='cuda'), coors, [64, 1440, 1440], 1)
+    rb = spconv.build_strided_rulebook(x)
+    idx = coors.cpu().numpy()
+    o_idx, o_shape, fwd, inv, _ = oracle.strided_map(idx, [64, 1440, 1440])
+    sub, _ = oracle.subm_map(idx, [64, 1440, 1440])
+    torch.manual_seed(0)
+    for nbr, ref_nbr, m_in, cin, cout in ((spconv.build_subm_rulebook(x).nbr, sub, coors.shape[0], 48, 48),
+                                          (rb.fwd_nbr, fwd, coors.shape[0], 48, 96),
+                                          (rb.inv_nbr, inv, rb.out_indices.shape[0], 96, 48)):
+        assert np.array_equal(nbr.cpu().numpy(), ref_nbr)
+        feats = torch.randn(m_in, cin).bfloat16()
+        w = (torch.randn(cout, 3, 3, 3, cin) * 0.05).bfloat16().float()
+        y = sparse_conv_forward(feats.cuda(), nbr, w.cuda(), None, _PackedWeights(), None, None, None, False)
+        ref = oracle.sparse_conv(feats.float(), ref_nbr, w)
+        err = (y.float().cpu() - ref).abs().max().item() / ref.abs().max().item()
+        assert err < 2e-2, (cin, cout, err)

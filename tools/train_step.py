@@ -24,7 +24,16 @@ def main():
     ap.add_argument('--steps', type=int, default=3)
     ap.add_argument('--warmup', type=int, default=1)
     ap.add_argument('--dtype', default='bf16')
-    args = ap.parse_args()
+    run(ap.parse_args())
+
+
+def bench_main(args):
+    """`python bench.py --mode train ...`: the same step under bench.py's JSON contract (frames per GPU from --frames,
+    default 8 -> use 2 for the train step unless the caller overrides it)."""
+    run(args, contract=True)
+
+
+def run(args, contract=False):
     rank, world = int(os.environ.get('RANK', '0')), int(os.environ.get('WORLD_SIZE', '1'))
     local = int(os.environ.get('LOCAL_RANK', '0'))
     torch.cuda.set_device(local)
@@ -59,12 +68,22 @@ def main():
         loss = step()
     e1.record()
     torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
     value, ms = throughput(pts.shape[0], e0.elapsed_time(e1), args.steps, 'cuda')
     if rank == 0:
-        print(json.dumps({'metric': 'points/sec, Waymo 1-sweep seg train step (fwd+bwd+SGD)', 'value': value,
-                          'unit': 'points/s', 'n_gpus': world, 'steps': args.steps, 'ms_per_step': ms / args.steps,
-                          'dtype': args.dtype, 'frames_per_gpu': args.frames, 'loss': float(loss.detach()),
-                          'peak_mem_gb': torch.cuda.max_memory_allocated() / 2 ** 30}), flush=True)
+        line = {'metric': 'points/sec, Waymo 1-sweep seg train step (fwd+bwd+SGD)', 'value': value,
+                'unit': 'points/s', 'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup,
+                'ms_per_step': ms / args.steps, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
+                'dtype': args.dtype, 'data': 'synthetic', 'frames_per_gpu': args.frames, 'loss': float(loss.detach()),
+                'peak_mem_gb': torch.cuda.max_memory_allocated() / 2 ** 30,
+                'config': {'workload': f'configs/waymo_one_sweep.yaml {args.dtype} training step (forward + backward + SGD), '
+                                       f'{args.frames} synthetic frames per GPU ({pts.shape[0]} points/GPU), '
+                                       'frame-parallel DDP gradient all-reduce over NCCL',
+                           'frames_per_gpu': args.frames, 'points_per_gpu': int(pts.shape[0]),
+                           'parallelism': f'DDP x{world}'}}
+        print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
 
