@@ -314,6 +314,18 @@ int os3d_window_attention_bf16_tc(const void *q, const void *k, const void *v, i
                                   const int32_t *level_info, const float *tau, float tau_min, void *out, int64_t ldo,
                                   void *stream);
 
+/* Second tensor-core design of the same attention (attention_v2.cu): one CTA per (128-query tile, group of heads whose
+ * slices make 96-128 columns), dedicated loader / MMA-issuer / softmax warps with mbarrier hand-offs, whole row slices
+ * fetched once for all heads of the group.  Same arguments and head-padded layout as os3d_window_attention_bf16_tc, but
+ * q and k must ALREADY be L2-normalised per head (os3d_qk_normalize with c = heads * dp, or the projection kernel's
+ * epilogue), and the softmax uses the fixed maximum 1 (unit vectors bound the scores): the caller must make sure that
+ * log2(e) / max(tau, tau_min) <= 60, i.e. max(tau, tau_min) >= 0.02405 -- below that use os3d_window_attention_bf16_tc
+ * (online maximum).  heads * dp must split into groups of 128 columns (dp = 16, 32) or 96 (dp = 48). */
+int os3d_window_attention_bf16_v2(const void *q, const void *k, const void *v, int64_t ld, int64_t ldv, int64_t m,
+                                  int heads, int dp, const int32_t *order, const int32_t *pos_seg,
+                                  const int32_t *level_info, const float *tau, float tau_min, void *out, int64_t ldo,
+                                  void *stream);
+
 /* out = resid + LayerNorm(x) * w + b over rows of c elements (c % 8 == 0); resid may be NULL; w, b f32.
  * replaces: norm1 / norm2 + the residual adds of EncoderLayer.forward (point_transformer_layer.py:288-298). */
 int os3d_layernorm_residual(const void *x, const void *resid, const float *w, const float *b, int64_t m, int c,

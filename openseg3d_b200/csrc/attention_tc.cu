@@ -54,7 +54,8 @@ __device__ __forceinline__ uint32_t core_off(int r, int c, int sbo) { return (r 
 // -- with KB = 32 and DP = 16 that is 64 columns, so 8 CTAs share an SM (and short windows waste half as many masked
 // score columns); KB = 64 otherwise (128 columns, 4 CTAs).
 //
-// ISSUER = 1 (experimental, OS3D_ATTN_ISSUER=1; not the default until it has been measured on a GPU): a fifth warp does
+// ISSUER = 1 (never instantiated: no launch path selects it, so it is not in the library; superseded by attention_v2.cu,
+// which is built around a dedicated issuer warp): a fifth warp does
 // nothing but issue the MMAs.  The four softmax warps then never execute a block-wide barrier in the key loop -- they
 // publish K / V (k_ready) and P (p_ready) with an mbarrier arrive and go on -- and warp 0 is no longer the straggler that
 // issues `UTCHMMA`s while the other three wait for it (ncu, ISSUER = 0: 24 % of the stall samples on those two barriers).
@@ -446,15 +447,6 @@ extern "C" int os3d_window_attention_bf16_tc(const void *q, const void *k, const
   cudaStream_t st = (cudaStream_t)stream;
   const char *e = getenv("OS3D_ATTN_KB");                       // tuning override: keys per block for dp = 16
   const bool kb32 = e ? atoi(e) != 64 : true;
-  const char *ei = getenv("OS3D_ATTN_ISSUER");                  // experimental variant with a dedicated MMA-issuing warp
-  if (ei && atoi(ei) == 1) {
-    const int th = attn_tc::kThreads + 32;
-    if (dp == 16) attn_tc::window_attention_tc_kernel<16, 32, 1><<<grid, th, 0, st>>>(p);
-    else if (dp == 32) attn_tc::window_attention_tc_kernel<32, 64, 1><<<grid, th, 0, st>>>(p);
-    else attn_tc::window_attention_tc_kernel<48, 64, 1><<<grid, th, 0, st>>>(p);
-    OS3D_LAUNCH_CHECK();
-    return 0;
-  }
   if (dp == 16 && kb32) attn_tc::window_attention_tc_kernel<16, 32><<<grid, attn_tc::kThreads, 0, st>>>(p);
   else if (dp == 16) attn_tc::window_attention_tc_kernel<16, 64><<<grid, attn_tc::kThreads, 0, st>>>(p);
   else if (dp == 32) attn_tc::window_attention_tc_kernel<32, 64><<<grid, attn_tc::kThreads, 0, st>>>(p);

@@ -23,6 +23,7 @@ from ..ops.linear import PackedLinearCache, linear_bf16
 from ..ops.mlp_chain import GELU as MLP_GELU, NONE as MLP_NONE, MlpChain, SwformerMlp
 
 _MLP_MODE = os.environ.get('OS3D_MLP_CHAIN', '1')
+_ATTN_IMPL = os.environ.get('OS3D_ATTN', 'v2')          # 'v1': attention_tc.cu for every layer (tuning / A-B runs)
 
 
 class WindowSegments(object):
@@ -428,10 +429,30 @@ class CosineMultiheadAttention(nn.MultiheadAttention):
         qk = F.linear(pos_dict.add_to(feat) if pos_dict is not None else feat, w_qk, b_qk)   # [M, 2*H*dp]: q | k
         v = F.linear(feat, w_v, b_v)                                                          # [M, H*dp]
         out = torch.empty((m, hd), dtype=feat.dtype, device=feat.device)
-        _lib.call('os3d_window_attention_bf16_tc', qk, qk.data_ptr() + hd * 2, v, 2 * hd, hd, m, self.num_heads, dp,
-                  seg.order, seg.pos_seg, seg.level_info, self.tau.detach().float().reshape(1), float(self.tau_min),
-                  out, hd, work=lambda: 4.0 * seg.sum_sq_tokens() * self.embed_dim)
+        work = lambda: _lib.Work(4.0 * seg.sum_sq_tokens() * self.embed_dim, 4 * m * hd * 2)     # noqa: E731  (q, k, v in; heads out)
+        k_ptr = _lib._Raw(qk.data_ptr() + hd * 2)
+        if _ATTN_IMPL == 'v2' and self._fixed_max_ok() and (self.num_heads * dp) % (96 if dp == 48 else 128) == 0:
+            # warp-specialised kernel, all heads of a group per CTA; q / k normalised beforehand, fixed-maximum softmax
+            _lib.call('os3d_qk_normalize', qk, k_ptr, 2 * hd, m, hd, self.num_heads, 2, work=lambda: 4 * m * hd * 2)
+            _lib.call('os3d_window_attention_bf16_v2', qk, k_ptr, v, 2 * hd, hd, m, self.num_heads, dp, seg.order,
+                      seg.pos_seg, seg.level_info, self.tau.detach().float().reshape(1), float(self.tau_min), out, hd,
+                      work=work)
+        else:
+            _lib.call('os3d_window_attention_bf16_tc', qk, k_ptr, v, 2 * hd, hd, m, self.num_heads, dp,
+                      seg.order, seg.pos_seg, seg.level_info, self.tau.detach().float().reshape(1), float(self.tau_min),
+                      out, hd, work=work)
         return out, o_c
+
+    def _fixed_max_ok(self):
+        """True when log2(e) / max(tau, tau_min) <= 60: unit-vector scores are then within 120 binades of the fixed softmax
+        maximum 1, so no row can underflow (os3d_window_attention_bf16_v2's precondition).  One host read of tau per
+        parameter version (constant at inference)."""
+        tag = (self.tau._version, self.tau.data_ptr())
+        hit = self.__dict__.get('_tau_ok')
+        if hit is None or hit[0] != tag:
+            t = max(float(self.tau.detach().float().reshape(-1)[0].item()), float(self.tau_min))
+            hit = self.__dict__['_tau_ok'] = (tag, 1.4426950408889634 / t <= 60.0)
+        return hit[1]
 
     def forward(self, query, key, value, key_padding_mask=None, need_weights=True, attn_mask=None):
         """The reference signature (cosine_msa.py:433-501) on padded windows: query / key / value [T, R, C] (sequence
