@@ -13,12 +13,12 @@
 //   work item : (128 consecutive positions of the window-grouped order, one GROUP of HG heads with HG * DP = 128 or 96
 //               columns).  Keys = the contiguous range of `order` from the start of the first touched window to the end
 //               of the last, walked in blocks of 64 keys.  A "unit" = (key block, head).
-//   warp 5    : loader.  cp.async (LDGSTS, 16 B) of WHOLE row slices (HG * DP * 2 = 192-256 B per row: all heads of the
+//   warp 9    : loader.  cp.async (LDGSTS, 16 B) of WHOLE row slices (HG * DP * 2 = 192-256 B per row: all heads of the
 //               group at once) of K and V for the next key block into a 2-stage ring, Q once; `order` is read once per
 //               key, not once per head.  Completion through cp.async.mbarrier.arrive.noinc.
-//   warp 4    : MMA issuer.  S = Q_h K_h^T into one of two TMEM score buffers, O_h += P V_h; MMA 1 of unit u+1 is issued
-//               before MMA 2 of unit u so the tensor pipe computes the next scores while the softmax warps work.
-//   warps 0-3 : softmax, thread = query row (tcgen05.ld 32x32b: lane = row).  Fixed-maximum softmax: q, k are unit
+//   warp 8    : MMA issuer.  S = Q_h K_h^T into one of four TMEM score buffers, O_h += P V_h; MMA 1 of unit u+4 is issued
+//               right after MMA 2 of unit u, so scores are ready two units before a warpgroup needs them.
+//   warps 0-7 : softmax, two warpgroups taking alternate units (even / odd heads), thread = query row (tcgen05.ld 32x32b: lane = row).  Fixed-maximum softmax: q, k are unit
 //               vectors, so every score is <= 1 and p = 2^(scale * (s - 1)) needs neither a running maximum nor a
 //               rescale of O; the host selects this kernel only when scale = log2(e) / max(tau, tau_min) <= 60 (no
 //               underflow of a whole row), else attention_tc.cu's online-maximum kernel runs.  Keys of other windows
@@ -27,8 +27,8 @@
 //               layout (lane = row: every STS.128 of a warp is one contiguous 512-byte run).
 //   hand-offs : mbarriers only (s_full / s_empty, p_full / p_empty, kv_full / kv_empty); no __syncthreads in the loop.
 //
-// Shared memory: Q 32 KB + 2 x (K 16 KB + V 16 KB) + P 16 KB = 112 KB -> 2 CTAs per SM; TMEM 256 columns per CTA
-// (2 x 64 scores + HG * DP output accumulators).
+// Shared memory: Q 32 KB + 2 x (K 16 KB + V 16 KB) + 4 x P 16 KB = 160 KB -> 1 CTA per SM with 8 softmax warps; TMEM
+// 4 x 64 score columns + HG * DP output accumulators (<= 384 of 512).
 #include "common.cuh"
 #include "tc_ptx.cuh"
 
@@ -38,7 +38,9 @@ using namespace ptx;
 
 constexpr int kTileQ = 128;
 constexpr int kKB = 64;                   // keys per block
-constexpr int kThreads = 192;             // 4 softmax warps + issuer + loader
+constexpr int kThreads = 352;             // 2 softmax warpgroups (8 warps) + 2 issuers + loader
+constexpr int kIssuer = 8, kLoader = 10;  // warp indices: issuer of warpgroup w is warp kIssuer + w
+constexpr int kNB = 4;                    // score buffers (TMEM) = P buffers (shared memory): unit u uses buffer u & 3
 
 struct Params {
   const __nv_bfloat16 *q, *k, *v;         // rows: q, k pitch ld (elements), v pitch ldv; head h at column h * dp; q, k normalised
@@ -50,6 +52,10 @@ struct Params {
   float tau_min;
   __nv_bfloat16 *out;
   int groups;                             // head groups per tile (heads / HG)
+  int vcs;                                // byte stride between 8-dim chunks of V in shared memory (= kKB * 16), passed at RUN TIME:
+                                          // with the V descriptor's SBO a compile-time constant nvcc 12.9 emitted MMA 2 with the P
+                                          // descriptor's high word for both operands (dims >= 8 of every head read from the wrong chunk;
+                                          // reproduced on B200, tools/debug_attn_v2.py) -- a value the compiler cannot fold avoids it
 };
 
 __device__ __forceinline__ float ex2_ftz(float x) {
@@ -62,24 +68,31 @@ __device__ __forceinline__ float ex2_ftz(float x) {
 // chunk of 8 consecutive columns of all rows is contiguous.  As a K-major operand (Q, K, P): LBO (between chunks along K)
 // = rows * 16, SBO (between 8-row groups) = 128.  As the MN-major B operand (V: N = head dims, K = keys): LBO (between
 // 8-key groups) = 128, SBO (between 8-dim groups) = rows * 16.
+//
+// Pipeline (measured first with ONE softmax warpgroup, a one-unit lookahead and a single P buffer: the softmax warps spent
+// 30 % of their time waiting for S -- every hand-off through the issuer costs ~800-1300 cycles (mbarrier wake-up, issue,
+// tensor pipe, commit, wake-up) against ~600-1000 cycles of softmax per unit, profiles/r02b_attn_v2_l2_first.txt): unit u
+// uses score buffer u & 3 (TMEM) and P buffer u & 3 (shared memory) and is handled by softmax warpgroup u & 1, so each
+// warpgroup has two units of slack on every hand-off: MMA 1 of unit u + 4 is issued right after MMA 2 of unit u.
 template <int HG, int DP>
-__global__ void __launch_bounds__(kThreads, 2) window_attention_v2_kernel(const Params p) {
+__global__ void __launch_bounds__(kThreads, 1) window_attention_v2_kernel(const Params p) {
   constexpr int kW = HG * DP;                          // columns of the group's row slice
   constexpr int kChunks = kW / 8;                      // 16-byte chunks per row slice
+  constexpr int kNS = HG == 2 ? 3 : 2;                 // K / V ring depth: the 4-unit lookahead may span (4 / HG) blocks
   constexpr int kQBytes = kChunks * kTileQ * 16;
   constexpr int kKVBytes = kChunks * kKB * 16;
   constexpr int kPBytes = (kKB / 8) * kTileQ * 16;
-  constexpr int kTmemCols = 256;
-  constexpr int kOCol = 2 * kKB;                       // O accumulators start after the two score buffers
-  static_assert(kW <= 128 && DP % 16 == 0, "head group too wide");
+  constexpr int kTmemCols = 512;
+  constexpr int kOCol = kNB * kKB;                     // O accumulators start after the score buffers
+  static_assert(kW <= 128 && DP % 16 == 0 && HG % 2 == 0, "head group");
 
   extern __shared__ __align__(1024) uint8_t smem[];
   uint8_t *q_s = smem;
-  uint8_t *k_s = q_s + kQBytes;                        // [2][kKVBytes]
-  uint8_t *v_s = k_s + 2 * kKVBytes;                   // [2][kKVBytes]
-  uint8_t *p_s = v_s + 2 * kKVBytes;
-  uint64_t *bars = reinterpret_cast<uint64_t *>(p_s + kPBytes);
-  uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 16);
+  uint8_t *k_s = q_s + kQBytes;                        // [kNS][kKVBytes]
+  uint8_t *v_s = k_s + kNS * kKVBytes;                 // [kNS][kKVBytes]
+  uint8_t *p_s = v_s + kNS * kKVBytes;                 // [kNB][kPBytes]
+  uint64_t *bars = reinterpret_cast<uint64_t *>(p_s + kNB * kPBytes);
+  uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 32);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   // groups of one query tile are adjacent in launch order: they run at the same time and share `order` / pos_seg lines
@@ -90,23 +103,22 @@ __global__ void __launch_bounds__(kThreads, 2) window_attention_v2_kernel(const 
   const int p_last = min(p0 + kTileQ, n_tok) - 1;
 
   const uint32_t q_full = smem_u32(&bars[0]), o_done = smem_u32(&bars[1]);
-  const uint32_t kv_full = smem_u32(&bars[2]), kv_empty = smem_u32(&bars[4]);      // [2] each, 8 bytes apart
-  const uint32_t s_full = smem_u32(&bars[6]), s_empty = smem_u32(&bars[8]);        // [2] each
-  const uint32_t p_full = smem_u32(&bars[10]), p_empty = smem_u32(&bars[11]);
+  const uint32_t kv_full = smem_u32(&bars[2]), kv_empty = smem_u32(&bars[5]);      // [kNS <= 3] each, 8 bytes apart
+  const uint32_t s_full = smem_u32(&bars[8]), p_full = smem_u32(&bars[12]);        // [kNB = 4] each
   if (tid == 0) {
     mbar_init(q_full, 32);
-    mbar_init(o_done, 1);
-    for (int i = 0; i < 2; ++i) {
+    mbar_init(o_done, 2);
+    for (int i = 0; i < kNS; ++i) {
       mbar_init(kv_full + 8 * i, 32);
-      mbar_init(kv_empty + 8 * i, 1);
-      mbar_init(s_full + 8 * i, 1);
-      mbar_init(s_empty + 8 * i, 4);
+      mbar_init(kv_empty + 8 * i, 2);
     }
-    mbar_init(p_full, 4);
-    mbar_init(p_empty, 1);
+    for (int i = 0; i < kNB; ++i) {
+      mbar_init(s_full + 8 * i, 1);
+      mbar_init(p_full + 8 * i, 4);
+    }
     fence_barrier_init();
   }
-  if (warp == 4) tmem_alloc(smem_u32(tmem_slot), kTmemCols);
+  if (warp == kIssuer) tmem_alloc(smem_u32(tmem_slot), kTmemCols);
 
   // key range of the tile: start of the first touched window .. end of the last touched window
   const int2 seg_first = __ldg(&p.pos_seg[p0]);
@@ -120,7 +132,7 @@ __global__ void __launch_bounds__(kThreads, 2) window_attention_v2_kernel(const 
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  if (warp == 5) {
+  if (warp == kLoader) {
     // ------------------------------------------------------------------ loader ----
     const int64_t col0 = (int64_t)g * kW;
     {  // Q tile: rows p0 .. p0+127 (zero-filled past the end); lane handles rows lane, lane+32, ...
@@ -137,9 +149,9 @@ __global__ void __launch_bounds__(kThreads, 2) window_attention_v2_kernel(const 
       }
       cp_async_mbar_arrive_noinc(q_full);
     }
+    int st = 0, use = 0;                             // ring stage of block b, how often that stage was used before
     for (int b = 0; b < n_blocks; ++b) {
-      const int st = b & 1;
-      if (b >= 2) mbar_wait(kv_empty + 8 * st, (uint32_t)((b >> 1) - 1) & 1u);
+      if (use > 0) mbar_wait(kv_empty + 8 * st, (uint32_t)(use - 1) & 1u);
       const uint32_t kd = smem_u32(k_s) + st * kKVBytes, vd = smem_u32(v_s) + st * kKVBytes;
 #pragma unroll
       for (int i = 0; i < kKB / 32; ++i) {
@@ -152,62 +164,78 @@ __global__ void __launch_bounds__(kThreads, 2) window_attention_v2_kernel(const 
 #pragma unroll
         for (int c = 0; c < kChunks; ++c) {
           cp_async_16(kd + c * (kKB * 16) + r * 16, ksrc + c * 8, ok ? 16u : 0u);
-          cp_async_16(vd + c * (kKB * 16) + r * 16, vsrc + c * 8, ok ? 16u : 0u);
+          cp_async_16(vd + c * p.vcs + r * 16, vsrc + c * 8, ok ? 16u : 0u);
         }
       }
       cp_async_mbar_arrive_noinc(kv_full + 8 * st);
+      if (++st == kNS) { st = 0; ++use; }
     }
-  } else if (warp == 4) {
-    // ------------------------------------------------------------------ MMA issuer ----
+  } else if (warp == kIssuer || warp == kIssuer + 1) {
+    // ------------------------------------------------------------------ MMA issuers ----
+    // One issuing warp per softmax warpgroup (units u = wg, wg + 2, ...): measured with ONE issuer per CTA, its serial
+    // work per unit (mbarrier wake-up, 5-8 UTCHMMA, tcgen05.commit) was the pace of the kernel.  The two issuers touch
+    // disjoint score / P buffers and disjoint output accumulators (even / odd heads), so no ordering between them is
+    // needed.  Per unit: wait p_full(u) -> O_h += P V_h -> S[u & 3] = Q K^T of unit u + 4 -> ONE commit (s_full of unit
+    // u + 4).  The tensor pipe executes one thread's MMAs in issue order, so that commit also says "MMA 2 of unit u has
+    // read P[u & 3]" -- the softmax warps need no separate p_empty / s_empty barriers: they write P(u + 4) only after
+    // they have seen s_full(u + 4), and MMA 1 of unit u + 4 is issued only after p_full(u) (every warp has read S(u)).
+    const int wg = warp - kIssuer;
     const uint32_t idesc1 = make_idesc_bf16(kTileQ, kKB);
     const uint32_t idesc2 = make_idesc_bf16(kTileQ, DP) | (1u << 16);          // bit 16: B (V) is MN-major
-    const uint64_t qd = make_kmajor_nosw_desc(smem_u32(q_s), kTileQ * 16, 128);
-    const uint64_t pd = make_kmajor_nosw_desc(smem_u32(p_s), kTileQ * 16, 128);
-    constexpr uint64_t kStepQ = (uint64_t)(2 * kTileQ * 16) >> 4;              // one K = 16 step (2 chunks) of Q / P
-    constexpr uint64_t kStepK = (uint64_t)(2 * kKB * 16) >> 4;                 // ... of K
-    constexpr uint64_t kStepV = (uint64_t)(2 * 128) >> 4;                      // 16 keys of V (MN-major: 8-key groups 128 B apart)
-    constexpr uint64_t kHeadQ = (uint64_t)((DP / 8) * kTileQ * 16) >> 4;       // next head's slice of Q
-    constexpr uint64_t kHeadKV = (uint64_t)((DP / 8) * kKB * 16) >> 4;         // ... of K / V
+    // descriptor words (tc_ptx.cuh: umma_bf16_words).  Start addresses advance in units of 16 bytes in the low word.
+    const uint32_t hi_k = nosw_desc_hi(128);                                   // K-major operands (Q, K, P): SBO = 128
+    const uint32_t hi_v = nosw_desc_hi((uint32_t)p.vcs);                       // V (MN-major): SBO = chunk stride
+    const uint32_t q_lo = nosw_desc_lo(smem_u32(q_s), kTileQ * 16);
+    constexpr uint32_t kStepQ = (2 * kTileQ * 16) >> 4;                        // one K = 16 step (2 chunks) of Q / P
+    constexpr uint32_t kStepK = (2 * kKB * 16) >> 4;                           // ... of K
+    constexpr uint32_t kStepV = (2 * 128) >> 4;                                // 16 keys of V (MN-major: 8-key groups 128 B apart)
+    constexpr uint32_t kHeadQ = ((DP / 8) * kTileQ * 16) >> 4;                 // next head's slice of Q
+    constexpr uint32_t kHeadK = ((DP / 8) * kKB * 16) >> 4;                    // ... of K
     mbar_wait(q_full, 0);
     fence_proxy_async();                 // LDGSTS (generic proxy) writes observed through the barrier -> visible to the MMA's async proxy
     tc_fence_after();
-    auto mma2 = [&](int u) {             // O_h += P V_h for unit u
-      const int b = u / HG, h = u - b * HG, st = b & 1;
-      mbar_wait(p_full, (uint32_t)u & 1u);
-      tc_fence_after();
-      const uint64_t vd = make_kmajor_nosw_desc(smem_u32(v_s) + st * kKVBytes, 128, kKB * 16) + h * kHeadKV;
-      if (elect_one()) {
-#pragma unroll
-        for (int s2 = 0; s2 < kKB / 16; ++s2)
-          umma_bf16(tmem_base + kOCol + h * DP, pd + s2 * kStepQ, vd + s2 * kStepV, idesc2, (b > 0 || s2 > 0) ? 1u : 0u);
-        umma_commit(p_empty);
-        if (h == HG - 1) umma_commit(kv_empty + 8 * st);
-        if (u == n_units - 1) umma_commit(o_done);
-      }
-      __syncwarp();
-    };
-    for (int u = 0; u < n_units; ++u) {
-      const int b = u / HG, h = u - b * HG, st = b & 1, sb = u & 1;
-      if (h == 0) {
-        mbar_wait(kv_full + 8 * st, (uint32_t)(b >> 1) & 1u);
+    int kv_seen = -1;                    // last block whose kv_full barrier has been waited for
+    auto mma1 = [&](int u) {             // S[u & 3] = Q_h K_h^T, then commit -> s_full[u & 3]
+      const int b = u / HG, h = u - b * HG, st = b % kNS, sb = u & (kNB - 1);
+      if (b > kv_seen) {
+        mbar_wait(kv_full + 8 * st, (uint32_t)(b / kNS) & 1u);
         fence_proxy_async();
+        tc_fence_after();
+        kv_seen = b;
       }
-      if (u >= 2) mbar_wait(s_empty + 8 * sb, (uint32_t)((u >> 1) - 1) & 1u);
-      tc_fence_after();
-      const uint64_t kd = make_kmajor_nosw_desc(smem_u32(k_s) + st * kKVBytes, kKB * 16, 128) + h * kHeadKV;
+      const uint32_t k_lo = nosw_desc_lo(smem_u32(k_s) + st * kKVBytes, kKB * 16) + h * kHeadK;
       if (elect_one()) {
 #pragma unroll
         for (int s = 0; s < DP / 16; ++s)
-          umma_bf16(tmem_base + sb * kKB, qd + h * kHeadQ + s * kStepQ, kd + s * kStepK, idesc1, s > 0 ? 1u : 0u);
+          umma_bf16_words(tmem_base + sb * kKB, q_lo + h * kHeadQ + s * kStepQ, hi_k, k_lo + s * kStepK, hi_k, idesc1,
+                          s > 0 ? 1u : 0u);
         umma_commit(s_full + 8 * sb);
       }
       __syncwarp();
-      if (u > 0) mma2(u - 1);
+    };
+    for (int u = wg; u < kNB && u < n_units; u += 2) mma1(u);
+    for (int u = wg; u < n_units; u += 2) {
+      const int b = u / HG, h = u - b * HG, st = b % kNS, sb = u & (kNB - 1);
+      mbar_wait(p_full + 8 * sb, (uint32_t)(u >> 2) & 1u);
+      tc_fence_after();
+      const uint32_t v_lo = nosw_desc_lo(smem_u32(v_s) + st * kKVBytes + h * (DP / 8) * p.vcs, 128);
+      const uint32_t p_lo = nosw_desc_lo(smem_u32(p_s) + sb * kPBytes, kTileQ * 16);
+      if (elect_one()) {
+#pragma unroll
+        for (int s2 = 0; s2 < kKB / 16; ++s2)
+          umma_bf16_words(tmem_base + kOCol + h * DP, p_lo + s2 * kStepQ, hi_k, v_lo + s2 * kStepV, hi_v, idesc2,
+                          (b > 0 || s2 > 0) ? 1u : 0u);
+        if (h >= HG - 2) umma_commit(kv_empty + 8 * st);          // this issuer's last head of the block (count 2: both issuers)
+        if (u + 2 >= n_units) umma_commit(o_done);                // this issuer's last unit
+      }
+      __syncwarp();
+      if (u + kNB < n_units) mma1(u + kNB);
     }
-    mma2(n_units - 1);
   } else {
     // ------------------------------------------------------------------ softmax warps ----
-    const int qp = p0 + tid;
+    const int wg = warp >> 2;              // warpgroup 0 takes the even units (heads), warpgroup 1 the odd ones
+    const int row = tid & 127;
+    const int qp = p0 + row;
     const bool q_ok = qp <= p_last;
     int qws = 0, qlen = 0;                 // this row's window = grouped positions [qws, qws + qlen)
     int32_t qrow = 0;
@@ -217,16 +245,15 @@ __global__ void __launch_bounds__(kThreads, 2) window_attention_v2_kernel(const 
       qlen = seg.y;
       qrow = __ldg(p.order + qp);
     }
-    const uint32_t tmem_row = tmem_base + ((uint32_t)(warp * 32) << 16);
+    const uint32_t tmem_row = tmem_base + ((uint32_t)((warp & 3) * 32) << 16);
     const float scale = 1.4426950408889634f / fmaxf(__ldg(p.tau), p.tau_min);
     const float neg_scale = -scale;
-    float l_run[HG];
+    float l_run[HG / 2];
 #pragma unroll
-    for (int h = 0; h < HG; ++h) l_run[h] = 0.0f;
+    for (int h = 0; h < HG / 2; ++h) l_run[h] = 0.0f;
 
     uint32_t v_lo = 0, v_hi = 0;
     bool warp_has_keys = false, all_valid = false;
-    int u = 0;
     for (int b = 0; b < n_blocks; ++b) {
       {  // valid keys of this block for this row: the index range [lo, hi) as a bit mask
         const int kb0 = ks + b * kKB;
@@ -238,11 +265,16 @@ __global__ void __launch_bounds__(kThreads, 2) window_attention_v2_kernel(const 
         all_valid = __all_sync(0xffffffffu, valid == ~0ull);
       }
 #pragma unroll
-      for (int h = 0; h < HG; ++h, ++u) {
-        const int sb = u & 1;
+      for (int hh = 0; hh < HG / 2; ++hh) {
+        const int u = b * HG + 2 * hh + wg;                       // this warpgroup's unit: head 2 * hh + wg
+        const int sb = u & (kNB - 1);
+        const uint32_t par = (uint32_t)(u >> 2) & 1u;
         uint32_t pk[kKB / 2];
+        // EVERY warp waits for the unit's scores, also one that will not read them: a warp that skipped the wait could reach
+        // the buffer's NEXT use before this phase completes, and mbarrier parity waits cannot tell "two phases ahead" from
+        // "done" (seen on hardware: rows that skipped block 0 read block 1's scores before MMA 1 had been issued)
+        mbar_wait(s_full + 8 * sb, par);
         if (warp_has_keys) {
-          mbar_wait(s_full + 8 * sb, (uint32_t)(u >> 1) & 1u);
           tc_fence_after();
           float s[kKB];
           {
@@ -256,9 +288,6 @@ __global__ void __launch_bounds__(kThreads, 2) window_attention_v2_kernel(const 
               s[32 + i] = __uint_as_float(r1[i]);
             }
           }
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(s_empty + 8 * sb);          // the score buffer may be overwritten by MMA 1 of unit u + 2
           if (!all_valid) {
 #pragma unroll
             for (int j = 0; j < kKB; ++j) {
@@ -271,24 +300,24 @@ __global__ void __launch_bounds__(kThreads, 2) window_attention_v2_kernel(const 
           for (int j = 0; j < kKB; j += 2) {
             const float a = ex2_ftz(fmaf(s[j], scale, neg_scale)), b2 = ex2_ftz(fmaf(s[j + 1], scale, neg_scale));
             l_blk += a + b2;
-            const __nv_bfloat162 hh = __floats2bfloat162_rn(a, b2);
-            pk[j >> 1] = *reinterpret_cast<const uint32_t *>(&hh);
+            const __nv_bfloat162 hv = __floats2bfloat162_rn(a, b2);
+            pk[j >> 1] = *reinterpret_cast<const uint32_t *>(&hv);
           }
-          l_run[h] += l_blk;
+          l_run[hh] += l_blk;
         } else {
-          // no row of this warp sees this key block: P rows are zero, the score buffer is released unread
-          if (lane == 0) mbar_arrive(s_empty + 8 * sb);
+          // no row of this warp sees this key block: P rows are zero, the scores stay unread
 #pragma unroll
           for (int i = 0; i < kKB / 2; ++i) pk[i] = 0u;
         }
-        if (u > 0) mbar_wait(p_empty, (uint32_t)(u - 1) & 1u);   // MMA 2 of the previous unit has read P
+        // P[sb] is free: s_full(u) was committed after MMA 2 of unit u - 4 (same issuing thread, in-order tensor pipe)
+        uint8_t *pdst = p_s + sb * kPBytes + row * 16;
 #pragma unroll
         for (int c = 0; c < kKB / 8; ++c)
-          *reinterpret_cast<uint4 *>(p_s + c * (kTileQ * 16) + tid * 16) =
-              make_uint4(pk[4 * c], pk[4 * c + 1], pk[4 * c + 2], pk[4 * c + 3]);
+          *reinterpret_cast<uint4 *>(pdst + c * (kTileQ * 16)) = make_uint4(pk[4 * c], pk[4 * c + 1], pk[4 * c + 2], pk[4 * c + 3]);
         fence_proxy_async();
+        tc_fence_before();                                       // orders this warp's tcgen05.ld of S(u) before MMA 1 of unit u + 4
         __syncwarp();
-        if (lane == 0) mbar_arrive(p_full);
+        if (lane == 0) mbar_arrive(p_full + 8 * sb);
       }
     }
 
@@ -297,8 +326,9 @@ __global__ void __launch_bounds__(kThreads, 2) window_attention_v2_kernel(const 
     tc_fence_after();
     __nv_bfloat16 *dst = p.out + (int64_t)qrow * p.ldo + (int64_t)g * kW;
 #pragma unroll
-    for (int h = 0; h < HG; ++h) {
-      const float inv_l = l_run[h] > 0.0f ? 1.0f / l_run[h] : 0.0f;
+    for (int hh = 0; hh < HG / 2; ++hh) {
+      const int h = 2 * hh + wg;
+      const float inv_l = l_run[hh] > 0.0f ? 1.0f / l_run[hh] : 0.0f;
 #pragma unroll
       for (int c0 = 0; c0 < DP; c0 += 16) {
         uint32_t o[16];
@@ -308,8 +338,8 @@ __global__ void __launch_bounds__(kThreads, 2) window_attention_v2_kernel(const 
           uint32_t w[8];
 #pragma unroll
           for (int i = 0; i < 8; ++i) {
-            const __nv_bfloat162 hh = __floats2bfloat162_rn(__uint_as_float(o[2 * i]) * inv_l, __uint_as_float(o[2 * i + 1]) * inv_l);
-            w[i] = *reinterpret_cast<const uint32_t *>(&hh);
+            const __nv_bfloat162 hv = __floats2bfloat162_rn(__uint_as_float(o[2 * i]) * inv_l, __uint_as_float(o[2 * i + 1]) * inv_l);
+            w[i] = *reinterpret_cast<const uint32_t *>(&hv);
           }
           reinterpret_cast<uint4 *>(dst + h * DP + c0)[0] = make_uint4(w[0], w[1], w[2], w[3]);
           reinterpret_cast<uint4 *>(dst + h * DP + c0)[1] = make_uint4(w[4], w[5], w[6], w[7]);
@@ -319,7 +349,7 @@ __global__ void __launch_bounds__(kThreads, 2) window_attention_v2_kernel(const 
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 4) {
+  if (warp == kIssuer) {
     tc_fence_after();
     tmem_dealloc(tmem_base, kTmemCols);
   }
@@ -329,7 +359,9 @@ template <int HG, int DP>
 int launch(const Params &p, int64_t m, int heads, cudaStream_t st) {
   constexpr int kW = HG * DP;
   constexpr int kChunks = kW / 8;
-  constexpr size_t smem = (size_t)kChunks * kTileQ * 16 + 4 * (size_t)kChunks * kKB * 16 + (kKB / 8) * kTileQ * 16 + 16 * 8 + 16;
+  constexpr int kNS = HG == 2 ? 3 : 2;
+  constexpr size_t smem = (size_t)kChunks * kTileQ * 16 + 2 * (size_t)kNS * kChunks * kKB * 16 +
+                          (size_t)kNB * (kKB / 8) * kTileQ * 16 + 32 * 8 + 16;
   static int configured_dev[64] = {0};
   int dev = 0;
   OS3D_CUDA(cudaGetDevice(&dev));
@@ -339,6 +371,7 @@ int launch(const Params &p, int64_t m, int heads, cudaStream_t st) {
   }
   Params q = p;
   q.groups = heads / HG;
+  q.vcs = kKB * 16;
   dim3 grid((unsigned)(cdiv(m, kTileQ) * q.groups));
   window_attention_v2_kernel<HG, DP><<<grid, kThreads, smem, st>>>(q);
   OS3D_LAUNCH_CHECK();

@@ -92,6 +92,25 @@ __device__ __forceinline__ void umma_bf16_lo(uint32_t tmem_d, uint32_t a_lo, uin
       "}" ::"r"(tmem_d), "r"(a_lo), "r"(b_lo), "r"(desc_hi), "r"(idesc), "r"(accum)
       : "memory");
 }
+// the general form: each descriptor given as its two 32-bit words (lo = start address >> 4 | LBO >> 4 << 16, hi = SBO >> 4 |
+// version / layout bits).  attention_v2.cu builds every descriptor this way: with 64-bit descriptors whose LBO / SBO
+// fields were compile-time constants nvcc 12.9 produced MMAs that read the wrong core matrices (reproduced on B200).
+__device__ __forceinline__ void umma_bf16_words(uint32_t tmem_d, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo, uint32_t b_hi,
+                                                uint32_t idesc, uint32_t accum) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      ".reg .b64 da, db;\n\t"
+      "mov.b64 da, {%1, %2};\n\t"
+      "mov.b64 db, {%3, %4};\n\t"
+      "setp.ne.b32 p, %6, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, p;\n\t"
+      "}" ::"r"(tmem_d), "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accum)
+      : "memory");
+}
+// words of a no-swizzle (INTERLEAVE) descriptor
+__device__ __forceinline__ uint32_t nosw_desc_lo(uint32_t saddr, uint32_t lbo) { return ((saddr & 0x3ffffu) >> 4) | ((lbo >> 4) << 16); }
+__device__ __forceinline__ uint32_t nosw_desc_hi(uint32_t sbo) { return (sbo >> 4) | (1u << 14); }
 // true in exactly one lane of a converged warp.  tcgen05.mma / commit are warp-uniform instructions: issuing them under
 // `if (lane == 0)` makes ptxas wrap each one in a per-lane election loop with R2UR moves (~10 instructions per MMA);
 // with the whole warp running the loop on uniform values and only the issue under elect.sync they compile to one UTCHMMA.
