@@ -38,9 +38,9 @@ using namespace ptx;
 
 constexpr int kTileQ = 128;
 constexpr int kKB = 64;                   // keys per block
-constexpr int kThreads = 352;             // 2 softmax warpgroups (8 warps) + 2 issuers + loader
-constexpr int kIssuer = 8, kLoader = 10;  // warp indices: issuer of warpgroup w is warp kIssuer + w
-constexpr int kNB = 4;                    // score buffers (TMEM) = P buffers (shared memory): unit u uses buffer u & 3
+constexpr int kThreads = 192;             // 4 softmax warps + issuer + loader
+constexpr int kIssuer = 4, kLoader = 5;   // warp indices
+constexpr int kNB = 2;                    // score buffers (TMEM): unit u uses buffer u & 1
 
 struct Params {
   const __nv_bfloat16 *q, *k, *v;         // rows: q, k pitch ld (elements), v pitch ldv; head h at column h * dp; q, k normalised
@@ -69,30 +69,36 @@ __device__ __forceinline__ float ex2_ftz(float x) {
 // = rows * 16, SBO (between 8-row groups) = 128.  As the MN-major B operand (V: N = head dims, K = keys): LBO (between
 // 8-key groups) = 128, SBO (between 8-dim groups) = rows * 16.
 //
-// Pipeline (measured first with ONE softmax warpgroup, a one-unit lookahead and a single P buffer: the softmax warps spent
-// 30 % of their time waiting for S -- every hand-off through the issuer costs ~800-1300 cycles (mbarrier wake-up, issue,
-// tensor pipe, commit, wake-up) against ~600-1000 cycles of softmax per unit, profiles/r02b_attn_v2_l2_first.txt): unit u
-// uses score buffer u & 3 (TMEM) and P buffer u & 3 (shared memory) and is handled by softmax warpgroup u & 1, so each
-// warpgroup has two units of slack on every hand-off: MMA 1 of unit u + 4 is issued right after MMA 2 of unit u.
+// Hand-off protocol (two mbarrier families per unit, ONE tcgen05.commit per unit):
+//   issuer  : MMA 1 of units 0, 1;  then per unit u:  wait p_full(u) -> O_h += P V_h -> S[u & 1] = Q K^T of unit u + 2 ->
+//             commit s_full[u & 1].  The tensor pipe executes one thread's MMAs in issue order, so that commit also says
+//             "MMA 2 of unit u has read P" and "S[u & 1] holds unit u + 2".  (A commit is issued even when unit u + 2
+//             does not exist: the last units need it as the P-free signal.)
+//   softmax : wait s_full(u) -> tcgen05.ld -> exponentials -> wait s_full(u + 1) (= MMA 2 of unit u - 1 has read the
+//             single P buffer; the scores of unit u + 1 arrive with the same signal) -> P -> fence -> arrive p_full(u).
+// Measured alternatives (profiles/r02b_*, r02c_*): separate s_empty / p_empty barriers (two more commits per unit: the
+// issuer became the pacer); one resident CTA with two softmax warpgroups and two issuers (prologue, Q load and epilogue
+// of the only CTA on the SM are exposed: 25 % of all stall samples).  Two co-resident CTAs overlap each other's
+// start-up, epilogue and hand-off latencies.
 template <int HG, int DP>
-__global__ void __launch_bounds__(kThreads, 1) window_attention_v2_kernel(const Params p) {
+__global__ void __launch_bounds__(kThreads, 2) window_attention_v2_kernel(const Params p) {
   constexpr int kW = HG * DP;                          // columns of the group's row slice
   constexpr int kChunks = kW / 8;                      // 16-byte chunks per row slice
-  constexpr int kNS = HG == 2 ? 3 : 2;                 // K / V ring depth: the 4-unit lookahead may span (4 / HG) blocks
+  constexpr int kNS = 2;                               // K / V ring depth
   constexpr int kQBytes = kChunks * kTileQ * 16;
   constexpr int kKVBytes = kChunks * kKB * 16;
   constexpr int kPBytes = (kKB / 8) * kTileQ * 16;
-  constexpr int kTmemCols = 512;
+  constexpr int kTmemCols = 256;
   constexpr int kOCol = kNB * kKB;                     // O accumulators start after the score buffers
-  static_assert(kW <= 128 && DP % 16 == 0 && HG % 2 == 0, "head group");
+  static_assert(kW <= 128 && DP % 16 == 0, "head group");
 
   extern __shared__ __align__(1024) uint8_t smem[];
   uint8_t *q_s = smem;
   uint8_t *k_s = q_s + kQBytes;                        // [kNS][kKVBytes]
   uint8_t *v_s = k_s + kNS * kKVBytes;                 // [kNS][kKVBytes]
-  uint8_t *p_s = v_s + kNS * kKVBytes;                 // [kNB][kPBytes]
-  uint64_t *bars = reinterpret_cast<uint64_t *>(p_s + kNB * kPBytes);
-  uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 32);
+  uint8_t *p_s = v_s + kNS * kKVBytes;                 // [kPBytes]
+  uint64_t *bars = reinterpret_cast<uint64_t *>(p_s + kPBytes);
+  uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 16);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   // groups of one query tile are adjacent in launch order: they run at the same time and share `order` / pos_seg lines
@@ -103,19 +109,17 @@ __global__ void __launch_bounds__(kThreads, 1) window_attention_v2_kernel(const 
   const int p_last = min(p0 + kTileQ, n_tok) - 1;
 
   const uint32_t q_full = smem_u32(&bars[0]), o_done = smem_u32(&bars[1]);
-  const uint32_t kv_full = smem_u32(&bars[2]), kv_empty = smem_u32(&bars[5]);      // [kNS <= 3] each, 8 bytes apart
-  const uint32_t s_full = smem_u32(&bars[8]), p_full = smem_u32(&bars[12]);        // [kNB = 4] each
+  const uint32_t kv_full = smem_u32(&bars[2]), kv_empty = smem_u32(&bars[4]);      // [kNS] each, 8 bytes apart
+  const uint32_t s_full = smem_u32(&bars[6]), p_full = smem_u32(&bars[8]);         // s_full[kNB = 2], p_full
   if (tid == 0) {
     mbar_init(q_full, 32);
-    mbar_init(o_done, 2);
+    mbar_init(o_done, 1);
     for (int i = 0; i < kNS; ++i) {
       mbar_init(kv_full + 8 * i, 32);
-      mbar_init(kv_empty + 8 * i, 2);
+      mbar_init(kv_empty + 8 * i, 1);
     }
-    for (int i = 0; i < kNB; ++i) {
-      mbar_init(s_full + 8 * i, 1);
-      mbar_init(p_full + 8 * i, 4);
-    }
+    for (int i = 0; i < kNB; ++i) mbar_init(s_full + 8 * i, 1);
+    mbar_init(p_full, 4);
     fence_barrier_init();
   }
   if (warp == kIssuer) tmem_alloc(smem_u32(tmem_slot), kTmemCols);
@@ -149,9 +153,9 @@ __global__ void __launch_bounds__(kThreads, 1) window_attention_v2_kernel(const 
       }
       cp_async_mbar_arrive_noinc(q_full);
     }
-    int st = 0, use = 0;                             // ring stage of block b, how often that stage was used before
     for (int b = 0; b < n_blocks; ++b) {
-      if (use > 0) mbar_wait(kv_empty + 8 * st, (uint32_t)(use - 1) & 1u);
+      const int st = b & 1;
+      if (b >= 2) mbar_wait(kv_empty + 8 * st, (uint32_t)((b >> 1) - 1) & 1u);
       const uint32_t kd = smem_u32(k_s) + st * kKVBytes, vd = smem_u32(v_s) + st * kKVBytes;
 #pragma unroll
       for (int i = 0; i < kKB / 32; ++i) {
@@ -168,24 +172,16 @@ __global__ void __launch_bounds__(kThreads, 1) window_attention_v2_kernel(const 
         }
       }
       cp_async_mbar_arrive_noinc(kv_full + 8 * st);
-      if (++st == kNS) { st = 0; ++use; }
     }
-  } else if (warp == kIssuer || warp == kIssuer + 1) {
-    // ------------------------------------------------------------------ MMA issuers ----
-    // One issuing warp per softmax warpgroup (units u = wg, wg + 2, ...): measured with ONE issuer per CTA, its serial
-    // work per unit (mbarrier wake-up, 5-8 UTCHMMA, tcgen05.commit) was the pace of the kernel.  The two issuers touch
-    // disjoint score / P buffers and disjoint output accumulators (even / odd heads), so no ordering between them is
-    // needed.  Per unit: wait p_full(u) -> O_h += P V_h -> S[u & 3] = Q K^T of unit u + 4 -> ONE commit (s_full of unit
-    // u + 4).  The tensor pipe executes one thread's MMAs in issue order, so that commit also says "MMA 2 of unit u has
-    // read P[u & 3]" -- the softmax warps need no separate p_empty / s_empty barriers: they write P(u + 4) only after
-    // they have seen s_full(u + 4), and MMA 1 of unit u + 4 is issued only after p_full(u) (every warp has read S(u)).
-    const int wg = warp - kIssuer;
+  } else if (warp == kIssuer) {
+    // ------------------------------------------------------------------ MMA issuer ----
     const uint32_t idesc1 = make_idesc_bf16(kTileQ, kKB);
     const uint32_t idesc2 = make_idesc_bf16(kTileQ, DP) | (1u << 16);          // bit 16: B (V) is MN-major
     // descriptor words (tc_ptx.cuh: umma_bf16_words).  Start addresses advance in units of 16 bytes in the low word.
     const uint32_t hi_k = nosw_desc_hi(128);                                   // K-major operands (Q, K, P): SBO = 128
     const uint32_t hi_v = nosw_desc_hi((uint32_t)p.vcs);                       // V (MN-major): SBO = chunk stride
     const uint32_t q_lo = nosw_desc_lo(smem_u32(q_s), kTileQ * 16);
+    const uint32_t p_lo = nosw_desc_lo(smem_u32(p_s), kTileQ * 16);
     constexpr uint32_t kStepQ = (2 * kTileQ * 16) >> 4;                        // one K = 16 step (2 chunks) of Q / P
     constexpr uint32_t kStepK = (2 * kKB * 16) >> 4;                           // ... of K
     constexpr uint32_t kStepV = (2 * 128) >> 4;                                // 16 keys of V (MN-major: 8-key groups 128 B apart)
@@ -195,47 +191,50 @@ __global__ void __launch_bounds__(kThreads, 1) window_attention_v2_kernel(const 
     fence_proxy_async();                 // LDGSTS (generic proxy) writes observed through the barrier -> visible to the MMA's async proxy
     tc_fence_after();
     int kv_seen = -1;                    // last block whose kv_full barrier has been waited for
-    auto mma1 = [&](int u) {             // S[u & 3] = Q_h K_h^T, then commit -> s_full[u & 3]
-      const int b = u / HG, h = u - b * HG, st = b % kNS, sb = u & (kNB - 1);
-      if (b > kv_seen) {
-        mbar_wait(kv_full + 8 * st, (uint32_t)(b / kNS) & 1u);
-        fence_proxy_async();
-        tc_fence_after();
-        kv_seen = b;
-      }
-      const uint32_t k_lo = nosw_desc_lo(smem_u32(k_s) + st * kKVBytes, kKB * 16) + h * kHeadK;
-      if (elect_one()) {
+    auto mma1 = [&](int u) {             // S[u & 1] = Q_h K_h^T (if unit u exists), then commit -> s_full[u & 1]
+      const int sb = u & (kNB - 1);
+      if (u < n_units) {
+        const int b = u / HG, h = u - b * HG, st = b & 1;
+        if (b > kv_seen) {
+          mbar_wait(kv_full + 8 * st, (uint32_t)(b >> 1) & 1u);
+          fence_proxy_async();
+          tc_fence_after();
+          kv_seen = b;
+        }
+        const uint32_t k_lo = nosw_desc_lo(smem_u32(k_s) + st * kKVBytes, kKB * 16) + h * kHeadK;
+        if (elect_one()) {
 #pragma unroll
-        for (int s = 0; s < DP / 16; ++s)
-          umma_bf16_words(tmem_base + sb * kKB, q_lo + h * kHeadQ + s * kStepQ, hi_k, k_lo + s * kStepK, hi_k, idesc1,
-                          s > 0 ? 1u : 0u);
-        umma_commit(s_full + 8 * sb);
+          for (int s = 0; s < DP / 16; ++s)
+            umma_bf16_words(tmem_base + sb * kKB, q_lo + h * kHeadQ + s * kStepQ, hi_k, k_lo + s * kStepK, hi_k, idesc1,
+                            s > 0 ? 1u : 0u);
+          umma_commit(s_full + 8 * sb);
+        }
+      } else if (elect_one()) {
+        umma_commit(s_full + 8 * sb);    // no such unit: the commit only reports "MMA 2 of unit u - 2 is done"
       }
       __syncwarp();
     };
-    for (int u = wg; u < kNB && u < n_units; u += 2) mma1(u);
-    for (int u = wg; u < n_units; u += 2) {
-      const int b = u / HG, h = u - b * HG, st = b % kNS, sb = u & (kNB - 1);
-      mbar_wait(p_full + 8 * sb, (uint32_t)(u >> 2) & 1u);
+    mma1(0);
+    mma1(1);
+    for (int u = 0; u < n_units; ++u) {
+      const int b = u / HG, h = u - b * HG, st = b & 1;
+      mbar_wait(p_full, (uint32_t)u & 1u);
       tc_fence_after();
       const uint32_t v_lo = nosw_desc_lo(smem_u32(v_s) + st * kKVBytes + h * (DP / 8) * p.vcs, 128);
-      const uint32_t p_lo = nosw_desc_lo(smem_u32(p_s) + sb * kPBytes, kTileQ * 16);
       if (elect_one()) {
 #pragma unroll
         for (int s2 = 0; s2 < kKB / 16; ++s2)
           umma_bf16_words(tmem_base + kOCol + h * DP, p_lo + s2 * kStepQ, hi_k, v_lo + s2 * kStepV, hi_v, idesc2,
                           (b > 0 || s2 > 0) ? 1u : 0u);
-        if (h >= HG - 2) umma_commit(kv_empty + 8 * st);          // this issuer's last head of the block (count 2: both issuers)
-        if (u + 2 >= n_units) umma_commit(o_done);                // this issuer's last unit
+        if (h == HG - 1) umma_commit(kv_empty + 8 * st);
+        if (u == n_units - 1) umma_commit(o_done);
       }
       __syncwarp();
-      if (u + kNB < n_units) mma1(u + kNB);
+      if (u + 1 < n_units) mma1(u + 2);          // (the last unit needs no successor signal)
     }
   } else {
     // ------------------------------------------------------------------ softmax warps ----
-    const int wg = warp >> 2;              // warpgroup 0 takes the even units (heads), warpgroup 1 the odd ones
-    const int row = tid & 127;
-    const int qp = p0 + row;
+    const int qp = p0 + tid;
     const bool q_ok = qp <= p_last;
     int qws = 0, qlen = 0;                 // this row's window = grouped positions [qws, qws + qlen)
     int32_t qrow = 0;
@@ -245,79 +244,86 @@ __global__ void __launch_bounds__(kThreads, 1) window_attention_v2_kernel(const 
       qlen = seg.y;
       qrow = __ldg(p.order + qp);
     }
-    const uint32_t tmem_row = tmem_base + ((uint32_t)((warp & 3) * 32) << 16);
+    const uint32_t tmem_row = tmem_base + ((uint32_t)(warp * 32) << 16);
     const float scale = 1.4426950408889634f / fmaxf(__ldg(p.tau), p.tau_min);
     const float neg_scale = -scale;
-    float l_run[HG / 2];
+    float l_run[HG];
 #pragma unroll
-    for (int h = 0; h < HG / 2; ++h) l_run[h] = 0.0f;
+    for (int h = 0; h < HG; ++h) l_run[h] = 0.0f;
 
-    uint32_t v_lo = 0, v_hi = 0;
-    bool warp_has_keys = false, all_valid = false;
+    int u = 0;
     for (int b = 0; b < n_blocks; ++b) {
-      {  // valid keys of this block for this row: the index range [lo, hi) as a bit mask
+      // valid keys of this block for this row: the index range [lo, hi) as a bit mask; per 16-key group: does ANY row of
+      // the warp see a key of the group (else its 16 scores are neither loaded nor exponentiated: windows are short, most
+      // of a 128 x 64 score tile lies off the block diagonal), do ALL rows see all of them (no masking needed)
+      uint64_t valid;
+      uint32_t grp_any = 0, grp_all = 0;
+      {
         const int kb0 = ks + b * kKB;
         const int lo = max(qws - kb0, 0), hi = min(qws + qlen - kb0, kKB);
-        const uint64_t valid = hi > lo ? ((~0ull >> (64 - (hi - lo))) << lo) : 0ull;
-        v_lo = (uint32_t)valid;
-        v_hi = (uint32_t)(valid >> 32);
-        warp_has_keys = __any_sync(0xffffffffu, valid != 0ull);
-        all_valid = __all_sync(0xffffffffu, valid == ~0ull);
+        valid = hi > lo ? ((~0ull >> (64 - (hi - lo))) << lo) : 0ull;
+#pragma unroll
+        for (int gq = 0; gq < kKB / 16; ++gq) {
+          const uint32_t bits = (uint32_t)(valid >> (16 * gq)) & 0xffffu;
+          grp_any |= (__any_sync(0xffffffffu, bits != 0u) ? 1u : 0u) << gq;
+          grp_all |= (__all_sync(0xffffffffu, bits == 0xffffu) ? 1u : 0u) << gq;
+        }
       }
 #pragma unroll
-      for (int hh = 0; hh < HG / 2; ++hh) {
-        const int u = b * HG + 2 * hh + wg;                       // this warpgroup's unit: head 2 * hh + wg
+      for (int h = 0; h < HG; ++h, ++u) {
         const int sb = u & (kNB - 1);
-        const uint32_t par = (uint32_t)(u >> 2) & 1u;
         uint32_t pk[kKB / 2];
         // EVERY warp waits for the unit's scores, also one that will not read them: a warp that skipped the wait could reach
         // the buffer's NEXT use before this phase completes, and mbarrier parity waits cannot tell "two phases ahead" from
         // "done" (seen on hardware: rows that skipped block 0 read block 1's scores before MMA 1 had been issued)
-        mbar_wait(s_full + 8 * sb, par);
-        if (warp_has_keys) {
+        mbar_wait(s_full + 8 * sb, (uint32_t)(u >> 1) & 1u);
+        float l_blk = 0.0f;
+        if (grp_any) {
           tc_fence_after();
-          float s[kKB];
-          {
-            uint32_t r0[32], r1[32];
-            tmem_ld32(tmem_row + sb * kKB, r0);
-            tmem_ld32(tmem_row + sb * kKB + 32, r1);
-            tmem_ld_wait();
+          uint32_t r[kKB / 16][16];
 #pragma unroll
-            for (int i = 0; i < 32; ++i) {
-              s[i] = __uint_as_float(r0[i]);
-              s[32 + i] = __uint_as_float(r1[i]);
+          for (int gq = 0; gq < kKB / 16; ++gq)
+            if ((grp_any >> gq) & 1u) tmem_ld16(tmem_row + sb * kKB + 16 * gq, r[gq]);
+          tmem_ld_wait();
+#pragma unroll
+          for (int gq = 0; gq < kKB / 16; ++gq) {
+            if ((grp_any >> gq) & 1u) {
+              const uint32_t bits = (uint32_t)(valid >> (16 * gq)) & 0xffffu;
+              const bool full = (grp_all >> gq) & 1u;
+#pragma unroll
+              for (int j = 0; j < 16; j += 2) {
+                float s0 = __uint_as_float(r[gq][j]), s1 = __uint_as_float(r[gq][j + 1]);
+                if (!full) {
+                  s0 = ((bits >> j) & 1u) ? s0 : -INFINITY;
+                  s1 = ((bits >> (j + 1)) & 1u) ? s1 : -INFINITY;
+                }
+                const float a = ex2_ftz(fmaf(s0, scale, neg_scale)), b2 = ex2_ftz(fmaf(s1, scale, neg_scale));
+                l_blk += a + b2;
+                const __nv_bfloat162 hv = __floats2bfloat162_rn(a, b2);
+                pk[8 * gq + (j >> 1)] = *reinterpret_cast<const uint32_t *>(&hv);
+              }
+            } else {
+#pragma unroll
+              for (int i = 0; i < 8; ++i) pk[8 * gq + i] = 0u;
             }
           }
-          if (!all_valid) {
-#pragma unroll
-            for (int j = 0; j < kKB; ++j) {
-              const bool ok = ((j < 32 ? v_lo : v_hi) >> (j & 31)) & 1u;
-              s[j] = ok ? s[j] : -INFINITY;
-            }
-          }
-          float l_blk = 0.0f;
-#pragma unroll
-          for (int j = 0; j < kKB; j += 2) {
-            const float a = ex2_ftz(fmaf(s[j], scale, neg_scale)), b2 = ex2_ftz(fmaf(s[j + 1], scale, neg_scale));
-            l_blk += a + b2;
-            const __nv_bfloat162 hv = __floats2bfloat162_rn(a, b2);
-            pk[j >> 1] = *reinterpret_cast<const uint32_t *>(&hv);
-          }
-          l_run[hh] += l_blk;
+          l_run[h] += l_blk;
         } else {
           // no row of this warp sees this key block: P rows are zero, the scores stay unread
 #pragma unroll
           for (int i = 0; i < kKB / 2; ++i) pk[i] = 0u;
         }
-        // P[sb] is free: s_full(u) was committed after MMA 2 of unit u - 4 (same issuing thread, in-order tensor pipe)
-        uint8_t *pdst = p_s + sb * kPBytes + row * 16;
+        // the single P buffer is free once MMA 2 of unit u - 1 has read it: that is what s_full(u + 1) reports (it also
+        // carries the next unit's scores, so the wait at the top of the next iteration returns at once)
+        if (u >= 1) mbar_wait(s_full + 8 * (sb ^ 1), (uint32_t)((u + 1) >> 1) & 1u);
 #pragma unroll
         for (int c = 0; c < kKB / 8; ++c)
-          *reinterpret_cast<uint4 *>(pdst + c * (kTileQ * 16)) = make_uint4(pk[4 * c], pk[4 * c + 1], pk[4 * c + 2], pk[4 * c + 3]);
+          *reinterpret_cast<uint4 *>(p_s + c * (kTileQ * 16) + tid * 16) =
+              make_uint4(pk[4 * c], pk[4 * c + 1], pk[4 * c + 2], pk[4 * c + 3]);
         fence_proxy_async();
-        tc_fence_before();                                       // orders this warp's tcgen05.ld of S(u) before MMA 1 of unit u + 4
+        tc_fence_before();                                       // orders this warp's tcgen05.ld of S(u) before MMA 1 of unit u + 2
         __syncwarp();
-        if (lane == 0) mbar_arrive(p_full + 8 * sb);
+        if (lane == 0) mbar_arrive(p_full);
       }
     }
 
@@ -326,9 +332,8 @@ __global__ void __launch_bounds__(kThreads, 1) window_attention_v2_kernel(const 
     tc_fence_after();
     __nv_bfloat16 *dst = p.out + (int64_t)qrow * p.ldo + (int64_t)g * kW;
 #pragma unroll
-    for (int hh = 0; hh < HG / 2; ++hh) {
-      const int h = 2 * hh + wg;
-      const float inv_l = l_run[hh] > 0.0f ? 1.0f / l_run[hh] : 0.0f;
+    for (int h = 0; h < HG; ++h) {
+      const float inv_l = l_run[h] > 0.0f ? 1.0f / l_run[h] : 0.0f;
 #pragma unroll
       for (int c0 = 0; c0 < DP; c0 += 16) {
         uint32_t o[16];
@@ -359,9 +364,7 @@ template <int HG, int DP>
 int launch(const Params &p, int64_t m, int heads, cudaStream_t st) {
   constexpr int kW = HG * DP;
   constexpr int kChunks = kW / 8;
-  constexpr int kNS = HG == 2 ? 3 : 2;
-  constexpr size_t smem = (size_t)kChunks * kTileQ * 16 + 2 * (size_t)kNS * kChunks * kKB * 16 +
-                          (size_t)kNB * (kKB / 8) * kTileQ * 16 + 32 * 8 + 16;
+  constexpr size_t smem = (size_t)kChunks * kTileQ * 16 + 4 * (size_t)kChunks * kKB * 16 + (size_t)(kKB / 8) * kTileQ * 16 + 16 * 8 + 16;
   static int configured_dev[64] = {0};
   int dev = 0;
   OS3D_CUDA(cudaGetDevice(&dev));

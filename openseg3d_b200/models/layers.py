@@ -23,7 +23,9 @@ from ..ops.linear import PackedLinearCache, linear_bf16
 from ..ops.mlp_chain import GELU as MLP_GELU, NONE as MLP_NONE, MlpChain, SwformerMlp
 
 _MLP_MODE = os.environ.get('OS3D_MLP_CHAIN', '1')
-_ATTN_IMPL = os.environ.get('OS3D_ATTN', 'v2')          # 'v1': attention_tc.cu for every layer (tuning / A-B runs)
+# 'v1' (default): attention_tc.cu, one CTA per (128-query tile, head), 4-8 CTAs per SM.  'v2': attention_v2.cu, the
+# warp-specialised all-heads-per-CTA design -- parity-tested, but measured slower at levels 1-2
+_ATTN_IMPL = os.environ.get('OS3D_ATTN', 'v1')
 
 
 class WindowSegments(object):

@@ -128,8 +128,9 @@ def _oracle_window_attention(x, coords, sparse_xyz, window, binfo, params, heads
     return oracle.window2flat(out3, info['inds'], x.shape[0])
 
 
+@pytest.mark.parametrize('impl', ['v1', 'v2'])
 @pytest.mark.parametrize('c,tau', [(48, 0.2), (96, 0.2), (192, 0.2), (384, 0.2), (96, 0.02), (192, 0.005)])
-def test_attention_tensor_core_bf16_vs_oracle(c, tau):
+def test_attention_tensor_core_bf16_vs_oracle(c, tau, impl, monkeypatch):
     """tcgen05 attention (bf16, head dims 6 / 12 / 24 / 48, in-kernel normalisation) against the ORACLE's padded cosine
     attention (cosine_msa.py:115-177 restated; fp32 on the same bf16-rounded inputs and weights); windows from 1 to
     several hundred tokens (multi key-block tiles, all four batching levels).  tau 0.2: fixed-maximum softmax (unit vectors
@@ -137,6 +138,9 @@ def test_attention_tensor_core_bf16_vs_oracle(c, tau):
     the model's temperatures; the sharp-softmax cases amplify the bf16 rounding of q / k / the scores and get 8e-2."""
     from openseg3d_b200 import spconv
     from openseg3d_b200.models import SparseWindowPartitionLayer, WindowAttention
+    from openseg3d_b200.models import layers as lay
+    # v1 = attention_tc.cu (default), v2 = attention_v2.cu (fixed-maximum softmax only: small tau falls back to v1)
+    monkeypatch.setattr(lay, '_ATTN_IMPL', impl)
     rng = np.random.default_rng(c)
     torch.manual_seed(c)
     binfo = {0: {'max_tokens': 16, 'batching_range': (0, 16)}, 1: {'max_tokens': 64, 'batching_range': (16, 64)},
