@@ -181,6 +181,22 @@ int os3d_linear_tc_bf16(const void *x, int64_t m, int k, int n, const void *w, c
                         const void *residual, const float *ln_gamma, const float *ln_beta, float ln_eps, const void *table,
                         const int32_t *tab_idx, int tab_cols, void *out, int64_t ldo, void *stream);
 
+/* Wide Linear layers with streamed weights and staged, coalesced stores (qkv_tc.cu):
+ *   y = x . W^T,  x [m, k] bf16 (k % 8 == 0, k <= 512),  W [n, k],  out [m, n] bf16 with row pitch ldo.
+ * The n output columns are processed in chunks of nc columns (os3d_wide_linear_plan(k, n, n_norm, dp, &nc) != 0 when the
+ * problem fits; nc is a multiple of dp that divides n and n_norm).  Columns [0, n_norm): y += table[tab_idx[r], col] (table
+ * bf16 [*, tab_ld]; NULL: y += bias) and, when `normalize`, every group of dp columns (one attention head) is L2-normalised
+ * (F.normalize, eps 1e-12).  Columns [n_norm, n): y += bias (NULL: nothing), then GELU (erf) when mode_rest == 2 (0: none).
+ * w_img: per chunk c the os3d_pack_linear_bf16 image of W[c*nc : (c+1)*nc, :], chunks concatenated.
+ * replaces: the q / k / v in-projections of cosine_multi_head_attention_forward with q = k = x + pos, v = x
+ *           (seg3d/models/layers/cosine_msa.py:48-63; point_transformer_layer.py:248) together with F.normalize of q and
+ *           k (cosine_msa.py:152-153); and MLP.fc1 + GELU (point_transformer_layer.py:260-276) where the hidden width
+ *           is beyond os3d_swformer_mlp_bf16. */
+int os3d_wide_linear_plan(int k, int n, int n_norm, int dp, int *nc);
+int os3d_wide_linear_bf16(const void *x, int64_t m, int k, int n, int dp, const void *w_img, const float *bias,
+                          const void *table, const int32_t *tab_idx, int64_t tab_ld, int n_norm, int normalize,
+                          int mode_rest, void *out, int64_t ldo, void *stream);
+
 /* A chain of 2..4 Linear layers in one persistent kernel (mlp_tc.cu), activations kept in shared / tensor memory:
  *   y = L_{n-1}(... act_0(L_0(a0))),  L_l(a) = a . W_l^T + b_l,  act: 0 none, 1 ReLU, 2 exact (erf) GELU.
  * a0 is either the bf16 matrix x [m, layers[0].k] (pitch ldx elements; x32 = NULL) or the output of an fp32 front layer

@@ -19,10 +19,11 @@ import torch.nn.functional as F
 from .. import _lib
 from .._lib import WindowCfg
 from ..ops.pooling import scatter_mean
-from ..ops.linear import PackedLinearCache, linear_bf16
+from ..ops.linear import PackedLinearCache, WideLinear, linear_bf16
 from ..ops.mlp_chain import GELU as MLP_GELU, NONE as MLP_NONE, MlpChain, SwformerMlp
 
 _MLP_MODE = os.environ.get('OS3D_MLP_CHAIN', '1')
+_QKV_MODE = os.environ.get('OS3D_QKV', '1')             # '0': in-projections as library GEMMs + separate table add (A-B runs)
 # 'v1' (default): attention_tc.cu, one CTA per (128-query tile, head), 4-8 CTAs per SM.  'v2': attention_v2.cu, the
 # warp-specialised all-heads-per-CTA design -- parity-tested, but measured slower at levels 1-2
 _ATTN_IMPL = os.environ.get('OS3D_ATTN', 'v1')
@@ -148,6 +149,33 @@ class KeyMaskDict(dict):
         return dict.get(self._ensure(), k, default)
 
 
+class _PartitionInfo(dict):
+    """The dict SparseWindowPartitionLayer.forward returns.  'voxel_coords' (indices as int64, point_transformer_layer.py:45)
+    and 'voxel_keep_inds' (arange: nothing is ever dropped) are materialised on first access -- the hot path reads neither."""
+
+    def __init__(self, indices):
+        super().__init__()
+        self._indices = indices
+
+    def __missing__(self, key):
+        if key == 'voxel_coords':
+            val = self._indices.long()
+        elif key == 'voxel_keep_inds':
+            val = torch.arange(self._indices.shape[0], device=self._indices.device, dtype=torch.long)
+        else:
+            raise KeyError(key)
+        self[key] = val
+        return val
+
+    def __contains__(self, key):
+        return key in ('voxel_coords', 'voxel_keep_inds') or dict.__contains__(self, key)
+
+    def keys(self):
+        for k in ('voxel_coords', 'voxel_keep_inds'):
+            self[k]
+        return dict.keys(self)
+
+
 class PosDict(dict):
     """``pos_dict_shift{i}``.  'flat' ([M, C] sinusoidal embedding, point_transformer_layer.py:152-207) is computed on
     first access: the bf16 hot path never needs it, because (x + pos) W^T = x W^T + pos W^T and pos takes only
@@ -170,11 +198,7 @@ class PosDict(dict):
         return self._layer.pos_table(self._c, self._seg.in_win.device)
 
     def table_as(self, dtype):
-        hit = self.__dict__.get('_tab_cast')
-        if hit is None or hit.dtype != dtype:
-            hit = self.table.to(dtype).contiguous()
-            self.__dict__['_tab_cast'] = hit
-        return hit
+        return self._layer.pos_table(self._c, self._seg.in_win.device, dtype)
 
     def add_to(self, x):
         """x + pos without materialising pos: one gather-add from the table (os3d_add_table_rows)."""
@@ -230,8 +254,13 @@ class SparseWindowPartitionLayer(nn.Module):
         return not all(ok[1:])
 
     @torch.no_grad()
-    def pos_table(self, feat_dim, device):
-        """fp32 embedding of every in-window position, row (z * win_y + y) * win_x + x."""
+    def pos_table(self, feat_dim, device, dtype=torch.float32):
+        """fp32 embedding of every in-window position, row (z * win_y + y) * win_x + x (cached, also per cast dtype)."""
+        if dtype != torch.float32:
+            ckey = (feat_dim, str(device), dtype)
+            if ckey not in self._tables:
+                self._tables[ckey] = self.pos_table(feat_dim, device).to(dtype).contiguous()
+            return self._tables[ckey]
         key = (feat_dim, str(device))
         if key not in self._tables:
             wx, wy, wz = [int(w) for w in self.window_shape]
@@ -301,9 +330,8 @@ class SparseWindowPartitionLayer(nn.Module):
         batch_size = getattr(x, 'batch_size', None)
         if batch_size is None:
             batch_size = int(indices[:, 0].max().item()) + 1
-        info = {'voxel_features': feats, 'voxel_coords': indices.long()}
-        m = indices.shape[0]
-        info['voxel_keep_inds'] = torch.arange(m, device=indices.device, dtype=torch.long)   # nothing is ever dropped
+        info = _PartitionInfo(indices)            # 'voxel_coords' / 'voxel_keep_inds' are built on first access
+        info['voxel_features'] = feats
         for i in range(2):
             seg = self.partition(indices, batch_size, i == 1)
             info[f'batch_win_inds_shift{i}'] = seg.win_id
@@ -426,24 +454,60 @@ class CosineMultiheadAttention(nn.MultiheadAttention):
         w_qk, b_qk, w_v, b_v, _, _, dp = self.params_head_padded(feat.dtype)
         o_c = self._out_proj_chunks()
         hd = self.num_heads * dp
-        # q / k / v projections are plain library GEMMs (cuBLAS); measured, os3d_linear_bf16 does not beat cuBLAS on
-        # them -- it is used where a fused epilogue removes whole passes (out-proj / fc2 + LayerNorm).
-        qk = F.linear(pos_dict.add_to(feat) if pos_dict is not None else feat, w_qk, b_qk)   # [M, 2*H*dp]: q | k
-        v = F.linear(feat, w_v, b_v)                                                          # [M, H*dp]
+        use_v2 = _ATTN_IMPL == 'v2' and self._fixed_max_ok() and (self.num_heads * dp) % (96 if dp == 48 else 128) == 0
+        proj = self._qkv_proj(pos_dict, use_v2) if isinstance(pos_dict, PosDict) else None
+        if proj is not None:
+            # ONE kernel: q | k | v = x [W_q | W_k | W_v]^T with the position term as a table row ((x + pos) W^T =
+            # x W^T + (pos W^T)[pos_idx], biases folded in), head-padded layout; q, k L2-normalised in its epilogue when
+            # the attention kernel expects that (v2) -- os3d_wide_linear_bf16, no library GEMM, no gather-add pass
+            lin, table = proj
+            qkv = lin(feat, table=table, tab_idx=pos_dict.pos_idx)                           # [M, 3*H*dp]: q | k | v
+            q_ptr, ld, ldv = qkv, 3 * hd, 3 * hd
+            k_ptr, v_ptr = _lib._Raw(qkv.data_ptr() + hd * 2), _lib._Raw(qkv.data_ptr() + 2 * hd * 2)
+            normalized = use_v2
+        else:
+            qk = F.linear(pos_dict.add_to(feat) if pos_dict is not None else feat, w_qk, b_qk)   # [M, 2*H*dp]: q | k
+            v_ptr = F.linear(feat, w_v, b_v)                                                      # [M, H*dp]
+            q_ptr, ld, ldv = qk, 2 * hd, hd
+            k_ptr = _lib._Raw(qk.data_ptr() + hd * 2)
+            normalized = False
         out = torch.empty((m, hd), dtype=feat.dtype, device=feat.device)
         work = lambda: _lib.Work(4.0 * seg.sum_sq_tokens() * self.embed_dim, 4 * m * hd * 2)     # noqa: E731  (q, k, v in; heads out)
-        k_ptr = _lib._Raw(qk.data_ptr() + hd * 2)
-        if _ATTN_IMPL == 'v2' and self._fixed_max_ok() and (self.num_heads * dp) % (96 if dp == 48 else 128) == 0:
+        tau = self.tau.detach().float().reshape(1)
+        if use_v2:
             # warp-specialised kernel, all heads of a group per CTA; q / k normalised beforehand, fixed-maximum softmax
-            _lib.call('os3d_qk_normalize', qk, k_ptr, 2 * hd, m, hd, self.num_heads, 2, work=lambda: 4 * m * hd * 2)
-            _lib.call('os3d_window_attention_bf16_v2', qk, k_ptr, v, 2 * hd, hd, m, self.num_heads, dp, seg.order,
-                      seg.pos_seg, seg.level_info, self.tau.detach().float().reshape(1), float(self.tau_min), out, hd,
-                      work=work)
+            if not normalized:
+                _lib.call('os3d_qk_normalize', q_ptr, k_ptr, ld, m, hd, self.num_heads, 2, work=lambda: 4 * m * hd * 2)
+            _lib.call('os3d_window_attention_bf16_v2', q_ptr, k_ptr, v_ptr, ld, ldv, m, self.num_heads, dp, seg.order,
+                      seg.pos_seg, seg.level_info, tau, float(self.tau_min), out, hd, work=work)
         else:
-            _lib.call('os3d_window_attention_bf16_tc', qk, k_ptr, v, 2 * hd, hd, m, self.num_heads, dp,
-                      seg.order, seg.pos_seg, seg.level_info, self.tau.detach().float().reshape(1), float(self.tau_min),
-                      out, hd, work=work)
+            _lib.call('os3d_window_attention_bf16_tc', q_ptr, k_ptr, v_ptr, ld, ldv, m, self.num_heads, dp,
+                      seg.order, seg.pos_seg, seg.level_info, tau, float(self.tau_min), out, hd, work=work)
         return out, o_c
+
+    def _qkv_proj(self, pos_dict, normalize=False):
+        """(WideLinear over [W_q | W_k | W_v] head-padded, position table [window volume, 2*H*dp] bf16 = pos W_qk^T + b_qk)
+        for this layer and this partition layer's embedding table, or None when the shape is outside the kernel.  Rebuilt
+        when a parameter changes."""
+        if _QKV_MODE == '0':
+            return None
+        pos_tab = pos_dict.table                                     # fp32 [volume, C], cached on the partition layer
+        tag = (self.in_proj_weight._version, self.in_proj_bias._version, self.in_proj_weight.data_ptr(), pos_tab.data_ptr(),
+               bool(normalize))
+        hit = self.__dict__.get('_qkv_hit')
+        if hit is None or hit[0] != tag:
+            w_qk, b_qk, w_v, b_v, _, _, dp = self.params_head_padded(torch.float32)
+            hd = self.num_heads * dp
+            val = None
+            gran = dp if normalize else 16        # epilogue granule: a whole head only when it has to be normalised
+            if WideLinear.fits(self.embed_dim, 3 * hd, 2 * hd, gran):
+                with torch.no_grad():
+                    w_all = torch.cat([w_qk, w_v], dim=0)                                        # [3*H*dp, C]
+                    bias = torch.cat([torch.zeros_like(b_qk), b_v])                              # q | k bias lives in the table
+                    table = (pos_tab @ w_qk.t() + b_qk).to(torch.bfloat16).contiguous()          # [volume, 2*H*dp]
+                    val = (WideLinear(w_all, bias, gran, n_norm=2 * hd, normalize=normalize), table)
+            hit = self.__dict__['_qkv_hit'] = (tag, val)
+        return hit[1]
 
     def _fixed_max_ok(self):
         """True when log2(e) / max(tau, tau_min) <= 60: unit-vector scores are then within 120 binades of the fixed softmax
@@ -583,7 +647,28 @@ def _cast_like(mod, name, dtype):
 
 
 def linear_in(mod, x):
-    """nn.Linear applied in x's dtype (cached weight copies) -- explicit bf16 instead of autocast."""
+    """nn.Linear applied in x's dtype (cached weight copies) -- explicit bf16 instead of autocast.  bf16 inference runs on
+    the persistent tcgen05 Linear kernel (os3d_linear_tc_bf16; out_features padded to a multiple of 16 with zero rows:
+    the 22-class voxel heads), everything else (fp32, training) on the library GEMM."""
+    n, k = mod.weight.shape
+    if (x.dtype == torch.bfloat16 and not torch.is_grad_enabled() and x.dim() == 2 and k % 8 == 0 and n <= 256
+            and x.is_cuda and x.shape[0] > 0):
+        hit = mod.__dict__.get('_os3d_tc')
+        tag = (mod.weight.data_ptr(), mod.weight._version, None if mod.bias is None else mod.bias._version)
+        if hit is None or hit[0] != tag:
+            n_pad = (n + 15) // 16 * 16
+            with torch.no_grad():
+                w = mod.weight.new_zeros((n_pad, k), dtype=torch.float32)
+                w[:n] = mod.weight.detach().float()
+                b = None
+                if mod.bias is not None:
+                    b = mod.weight.new_zeros(n_pad, dtype=torch.float32)
+                    b[:n] = mod.bias.detach().float()
+            chunks = PackedLinearCache().get('w', w, b, max_width=256)
+            hit = mod.__dict__['_os3d_tc'] = (tag, chunks if _lib.lib().os3d_linear_tc_fits(k, n_pad) else None)
+        if hit[1] is not None:
+            out = linear_bf16(x, hit[1])
+            return out if out.shape[1] == n else out[:, :n]
     return F.linear(x, _cast_like(mod, 'weight', x.dtype), _cast_like(mod, 'bias', x.dtype))
 
 
@@ -666,8 +751,12 @@ class EncoderLayer(nn.Module):
                 return chain(x1, residual=x1, ln=_ln_params(self.norm2))
             # wider layers (weights beyond shared memory): fc1 is a library GEMM + the in-place GELU kernel --
             # os3d_linear_bf16's GELU epilogue measured the same (L3: 0.29 ms vs 0.12 + 0.16 ms)
-            h = linear_in(self.mlp.fc1, x1)
-            _lib.call('os3d_gelu_bf16', h, h.numel(), h, work=lambda: 2 * h.numel() * 2)          # in place
+            fc1 = self._fc1_wide()
+            if fc1 is not None:
+                h = fc1(x1)                                                                      # fc1 + GELU, one kernel
+            else:
+                h = linear_in(self.mlp.fc1, x1)
+                _lib.call('os3d_gelu_bf16', h, h.numel(), h, work=lambda: 2 * h.numel() * 2)      # in place
             return linear_bf16(h, cache.get('fc2', self.mlp.fc2.weight, self.mlp.fc2.bias, max_width=512), residual=x1,
                                ln=_ln_params(self.norm2))
         attn = self.win_attn(x, pos_dict, ind_dict, key_padding_mask_dict)
@@ -677,6 +766,20 @@ class EncoderLayer(nn.Module):
         x = residual_layer_norm(self.norm1, attn, x)
         return residual_layer_norm(self.norm2, self.mlp(x), x)
 
+
+    def _fc1_wide(self):
+        """fc1 + GELU on os3d_wide_linear_bf16 for the layers whose MLP is beyond the fused kernel (level 4), or None."""
+        if _QKV_MODE == '0':
+            return None
+        fc1 = self.mlp.fc1
+        tag = (fc1.weight.data_ptr(), fc1.weight._version, fc1.bias._version)
+        hit = self.__dict__.get('_fc1_hit')
+        if hit is None or hit[0] != tag:
+            n, k = fc1.weight.shape
+            dp = next((d for d in (16, 32) if n % d == 0 and WideLinear.fits(k, n, 0, d)), None)
+            val = WideLinear(fc1.weight, fc1.bias, dp, gelu=True) if dp is not None else None
+            hit = self.__dict__['_fc1_hit'] = (tag, val)
+        return hit[1]
 
     def _mlp_chain(self):
         """The fused MLP + norm2 + residual kernel for this layer, or None when its width is beyond the kernels (C > 192).
@@ -730,7 +833,12 @@ class FlattenSELayer(nn.Module):
 
     def gate(self, x, indices, batch_size=None):
         """Per-frame channel gate [B, C] (fp32): sigmoid(fc(mean over the frame's points))."""
-        return self.fc(scatter_mean(x, indices.long(), batch_size).float())
+        pooled = scatter_mean(x, indices.long(), batch_size).float()
+        if torch.is_grad_enabled():
+            return self.fc(pooled)
+        # B rows x (C -> C / r -> C): two products of a handful of rows, done as broadcast multiply + reduce (no GEMM launch)
+        h = torch.relu((pooled[:, None, :] * self.fc[0].weight.float()[None]).sum(-1))
+        return torch.sigmoid((h[:, None, :] * self.fc[2].weight.float()[None]).sum(-1))
 
     def residual_forward(self, x, indices, batch_size=None):
         """x + forward(x) in one pass over the points (inference): x * (1 + gate[batch index])."""

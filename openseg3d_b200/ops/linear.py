@@ -90,3 +90,47 @@ class _Ptr(object):
 
     def __init__(self, t):
         self.ptr = t.data_ptr()
+
+
+class WideLinear(object):
+    """A wide Linear layer on os3d_wide_linear_bf16 (qkv_tc.cu): weights streamed in chunks of nc output columns, outputs
+    staged and stored coalesced.  ``weight`` [n, k] (fp32 / any float), ``dp``: head width -- the granule of the per-head
+    L2 normalisation of the first ``n_norm`` columns (the attention in-projection's q | k) or just the processing granule.
+    ``fits(k, n, n_norm, dp)`` says whether the kernel takes the shape."""
+
+    @staticmethod
+    def fits(k, n, n_norm, dp):
+        return bool(_lib.lib().os3d_wide_linear_plan(k, n, n_norm, dp, None))
+
+    def __init__(self, weight, bias, dp, n_norm=0, normalize=False, gelu=False):
+        n, k = weight.shape
+        nc = ctypes.c_int(0)
+        if not _lib.lib().os3d_wide_linear_plan(k, n, n_norm, dp, ctypes.byref(nc)):
+            raise RuntimeError(f'wide linear: shape k={k} n={n} dp={dp} does not fit os3d_wide_linear_bf16')
+        self.k, self.n, self.dp, self.nc, self.n_norm = k, n, dp, nc.value, n_norm
+        self.normalize, self.mode_rest = int(normalize), 2 if gelu else 0
+        w32 = weight.detach().float().contiguous()
+        elems = ctypes.c_int64(0)
+        _lib.lib().os3d_linear_bf16_packed_elems(k, self.nc, ctypes.byref(elems))
+        self.w_img = torch.empty((n // self.nc, elems.value), dtype=torch.bfloat16, device=weight.device)
+        for c in range(n // self.nc):
+            _lib.call('os3d_pack_linear_bf16', w32[c * self.nc:(c + 1) * self.nc].contiguous(), k, self.nc, self.w_img[c])
+        self.bias = None if bias is None else bias.detach().float().contiguous()
+
+    def __call__(self, x, table=None, tab_idx=None, out=None):
+        """x [m, k] bf16 -> [m, n] bf16.  table [rows, >= n_norm] bf16 + tab_idx int32 [m]: additive row term of the first
+        n_norm columns (replaces the bias there)."""
+        _lib.require_cuda(x)
+        if x.dtype != torch.bfloat16 or x.shape[1] != self.k:
+            raise RuntimeError('wide linear takes bfloat16 activations [m, k]')
+        x = x.contiguous()
+        m = x.shape[0]
+        if out is None:
+            out = torch.empty((m, self.n), dtype=torch.bfloat16, device=x.device)
+        if m:
+            _lib.call('os3d_wide_linear_bf16', x, m, self.k, self.n, self.dp, self.w_img, self.bias, table, tab_idx,
+                      table.shape[1] if table is not None else 0, self.n_norm, self.normalize, self.mode_rest, out,
+                      out.stride(0),
+                      work=lambda: _lib.Work(2.0 * m * self.k * self.n, 2.0 * (m * self.k + m * self.n + self.k * self.n)
+                                             + (4.0 * m + 2.0 * m * self.n_norm if table is not None else 0.0)))
+        return out

@@ -80,3 +80,55 @@ def test_gelu_bf16_matches_erf_gelu():
     big = ref.abs() > 1e-6                         # below that float64 erf saturates to exactly -1 (ref = -0.0)
     exact = (out.cpu()[big] == ref.bfloat16()[big]).float().mean().item()
     assert exact > 0.98, exact                       # measured 98.7 %: the rest differ by one bf16 ulp
+
+
+@pytest.mark.parametrize('k,heads,d,m', [(48, 8, 6, 1), (48, 8, 6, 70001), (96, 8, 12, 300), (192, 8, 24, 40000), (384, 8, 48, 20011)])
+@pytest.mark.parametrize('normalize', [False, True])
+def test_wide_linear_qkv_projection_matches_float64(k, heads, d, m, normalize):
+    """os3d_wide_linear_bf16 as the attention in-projection: q | k | v = x [Wq | Wk | Wv]^T with the position term as a
+    table row and (optionally) per-head L2 normalisation of q and k, head-padded layout -- against a float64 restatement
+    of cosine_msa.py:48-63 + :152-153 on the same bf16-rounded operands.  Ragged row counts (1 row, not a multiple of the
+    128-row tile), every level's width."""
+    import torch.nn.functional as F
+    from openseg3d_b200.ops.linear import WideLinear
+    torch.manual_seed(k + m)
+    dp = (d + 15) // 16 * 16
+    hd = heads * dp
+    x = torch.randn(m, k, device='cuda').bfloat16()
+    w = torch.zeros(3, heads, dp, k, device='cuda')
+    w[:, :, :d] = torch.randn(3, heads, d, k, device='cuda') / k ** 0.5
+    w = w.bfloat16().float().reshape(3 * hd, k)                       # head-padded rows: pad rows are zero
+    b_v = torch.zeros(heads, dp, device='cuda')
+    b_v[:, :d] = torch.randn(heads, d, device='cuda') * 0.1
+    bias = torch.cat([torch.zeros(2 * hd, device='cuda'), b_v.reshape(-1)])
+    table = torch.zeros(800, 2, heads, dp, device='cuda')
+    table[:, :, :, :d] = torch.randn(800, 2, heads, d, device='cuda') * 0.5
+    table = table.reshape(800, 2 * hd).bfloat16()
+    idx = torch.randint(0, 800, (m,), device='cuda', dtype=torch.int32)
+    lin = WideLinear(w, bias, dp if normalize else 16, n_norm=2 * hd, normalize=normalize)
+    out = lin(x, table=table, tab_idx=idx)
+    assert out.shape == (m, 3 * hd) and out.dtype == torch.bfloat16
+    ref = x.double() @ w.double().t()
+    ref[:, :2 * hd] += table.double()[idx.long()]
+    ref[:, 2 * hd:] += bias.double()[2 * hd:]
+    if normalize:
+        qk = F.normalize(ref[:, :2 * hd].reshape(m, 2 * heads, dp), dim=-1).reshape(m, 2 * hd)
+        ref = torch.cat([qk, ref[:, 2 * hd:]], dim=1)
+    err = (out.double() - ref).abs().max().item() / ref.abs().max().item()
+    assert err < 1e-2, err                                             # bf16 output rounding: 2^-9 of the value
+
+
+@pytest.mark.parametrize('m', [1, 128, 20011])
+def test_wide_linear_fc1_gelu_matches_float64(m):
+    """os3d_wide_linear_bf16 as MLP.fc1 + GELU of the level-4 layers (384 -> 768), point_transformer_layer.py:260-276."""
+    import torch.nn.functional as F
+    from openseg3d_b200.ops.linear import WideLinear
+    torch.manual_seed(m)
+    x = torch.randn(m, 384, device='cuda').bfloat16()
+    w = (torch.randn(768, 384, device='cuda') / 384 ** 0.5).bfloat16().float()
+    b = torch.randn(768, device='cuda') * 0.1
+    dp = next(d for d in (16, 32) if WideLinear.fits(384, 768, 0, d))
+    out = WideLinear(w, b, dp, gelu=True)(x)
+    ref = F.gelu(x.double() @ w.double().t() + b.double())
+    err = (out.double() - ref).abs().max().item() / ref.abs().max().item()
+    assert err < 1e-2, err
