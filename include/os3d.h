@@ -357,6 +357,13 @@ int os3d_layernorm_residual(const void *x, const void *resid, const float *w, co
 int os3d_knn_query(const float *xyz, const float *new_xyz, int64_t m, int nsample, const int32_t *offset,
                    const int32_t *new_offset, int n_seg, int32_t *idx, float *dist2, void *stream);
 
+/* Majority label of every voxel over its points (ties -> the lowest label, voxels without a labelled point -> ignore).
+ * pvid [n] int64 point -> voxel ids (-1 = outside), labels [n] uint8 in [0, 30] or == ignore (31 <= ignore <= 255);
+ * hist [m * 32] int32 scratch, bad: device int32[1] (set to 1 when a label outside that set was seen), out [m] uint8.
+ * replaces: WaymoDataset.prepare_voxel_labels (seg3d/datasets/waymo_dataset.py:213-246). */
+int os3d_voxel_majority_labels(const int64_t *pvid, const uint8_t *labels, int64_t n, int64_t m, int ignore, int32_t *hist,
+                               int32_t *bad, uint8_t *out, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

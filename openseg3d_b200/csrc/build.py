@@ -5,7 +5,7 @@ import sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 OUT = os.path.join(os.path.dirname(HERE), 'libos3d.so')
-SOURCES = ['voxelize.cu', 'scatter.cu', 'rulebook.cu', 'spconv_f32.cu', 'spconv_tc.cu', 'window.cu', 'attention.cu', 'attention_tc.cu', 'attention_v2.cu', 'norm.cu', 'knn.cu', 'linear_tc.cu', 'mlp_tc.cu', 'mlp2_tc.cu', 'qkv_tc.cu']
+SOURCES = ['voxelize.cu', 'scatter.cu', 'rulebook.cu', 'spconv_f32.cu', 'spconv_tc.cu', 'window.cu', 'attention.cu', 'attention_tc.cu', 'attention_v2.cu', 'norm.cu', 'knn.cu', 'linear_tc.cu', 'mlp_tc.cu', 'mlp2_tc.cu', 'qkv_tc.cu', 'labels.cu']
 NVCC_FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-O3', '-lineinfo', '-std=c++17', '-Xcompiler', '-fPIC',
               '--expt-relaxed-constexpr', '-Xptxas', '-v']
 

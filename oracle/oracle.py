@@ -235,6 +235,37 @@ def knn_query(nsample, xyz, new_xyz, offset, new_offset):
 # ------------------------------------------------------------------------------------------------
 # Stage 4 -- window partition (swformer_utils.py, point_transformer_layer.py)
 # ------------------------------------------------------------------------------------------------
+def voxel_majority_labels(point_voxel_ids, point_labels, num_voxels, ignore_index=255):
+    """WaymoDataset.prepare_voxel_labels, seg3d/datasets/waymo_dataset.py:213-246: a 256-bin counter per voxel over its
+    points (voxel_id != -1), np.argmax per voxel (first maximum = lowest label), voxels without a point -> ignore_index."""
+    ids = np.asarray(point_voxel_ids, np.int64)
+    lab = np.asarray(point_labels, np.int64)
+    counts = np.zeros((num_voxels, 256), dtype=np.int64)
+    keep = ids != -1
+    np.add.at(counts, (ids[keep], lab[keep]), 1)
+    out = np.full(num_voxels, ignore_index, dtype=np.uint8)
+    seen = counts.sum(axis=1) > 0
+    out[seen] = counts[seen].argmax(axis=1).astype(np.uint8)
+    return out
+
+
+def voxel_centers(coords_zyx, scale, voxel_size, pc_range):
+    """get_voxel_centers, seg3d/utils/pointops_utils.py:14-22 (float32 arithmetic in the same order)."""
+    c = np.asarray(coords_zyx)[:, [2, 1, 0]].astype(np.float32)
+    vs = np.asarray(voxel_size, np.float32) * np.float32(scale)
+    return (c + np.float32(0.5)) * vs + np.asarray(pc_range[:3], np.float32)
+
+
+def aux_voxel_labels(voxel_labels, voxel_coords, aux_voxel_coords, batch_size, voxel_size, pc_range, aux_scale=8.0):
+    """tools/train.py:86-104: aux voxel -> label of the nearest level-1 voxel centre of the same frame (knn_query, k = 1)."""
+    c1 = voxel_centers(np.asarray(voxel_coords)[:, 1:], 1.0, voxel_size, pc_range)
+    c8 = voxel_centers(np.asarray(aux_voxel_coords)[:, 1:], aux_scale, voxel_size, pc_range)
+    off = np.asarray([(np.asarray(voxel_coords)[:, 0] <= b).sum() for b in range(batch_size)], np.int32)
+    aoff = np.asarray([(np.asarray(aux_voxel_coords)[:, 0] <= b).sum() for b in range(batch_size)], np.int32)
+    idx, _ = knn_query(1, c1, c8, off, aoff)
+    return np.asarray(voxel_labels)[idx.reshape(-1)]
+
+
 def ingroup_rank(group):
     g = np.ascontiguousarray(group, np.int64)
     out = np.empty_like(g)
