@@ -284,7 +284,7 @@ def build_roofline(arm, by, recs, step_ms, pk):
         for k in hbm_names if k in by and by[k][1] > 0}
     roofline['hbm_peak_gbs'] = pk['hbm']
     # window attention: useful FLOPs = 4 * sum_windows n^2 * C (QK^T + PV over real tokens only; the reference pads to max_tokens)
-    for entry in ('os3d_window_attention_bf16_tc', 'os3d_window_attention_bf16_v2'):
+    for entry in ('os3d_window_attention_bf16_tc', 'os3d_window_attention_bf16_tc_prenorm', 'os3d_window_attention_bf16_v2'):
         at = by.get(entry)
         if at and at[0] and at[1]:
             roofline['window_attention_tc_kernel'] = {

@@ -330,6 +330,13 @@ int os3d_window_attention_bf16_tc(const void *q, const void *k, const void *v, i
                                   const int32_t *level_info, const float *tau, float tau_min, void *out, int64_t ldo,
                                   void *stream);
 
+/* The same kernel for q, k that are ALREADY L2-normalised per head (os3d_wide_linear_bf16 with normalize = 1): the gather
+ * is a plain copy. */
+int os3d_window_attention_bf16_tc_prenorm(const void *q, const void *k, const void *v, int64_t ld, int64_t ldv, int64_t m,
+                                          int heads, int dp, const int32_t *order, const int32_t *pos_seg,
+                                          const int32_t *level_info, const float *tau, float tau_min, void *out,
+                                          int64_t ldo, void *stream);
+
 /* Second tensor-core design of the same attention (attention_v2.cu): one CTA per (128-query tile, group of heads whose
  * slices make 96-128 columns), dedicated loader / MMA-issuer / softmax warps with mbarrier hand-offs, whole row slices
  * fetched once for all heads of the group.  Same arguments and head-padded layout as os3d_window_attention_bf16_tc, but

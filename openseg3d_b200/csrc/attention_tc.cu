@@ -59,7 +59,9 @@ __device__ __forceinline__ uint32_t core_off(int r, int c, int sbo) { return (r 
 // nothing but issue the MMAs.  The four softmax warps then never execute a block-wide barrier in the key loop -- they
 // publish K / V (k_ready) and P (p_ready) with an mbarrier arrive and go on -- and warp 0 is no longer the straggler that
 // issues `UTCHMMA`s while the other three wait for it (ncu, ISSUER = 0: 24 % of the stall samples on those two barriers).
-template <int DP, int KB, int ISSUER = 0>
+// PRENORM = 1: q and k arrive already L2-normalised per head (the in-projection kernel's epilogue, qkv_tc.cu): the gather
+// is a plain copy -- the per-(tile, head) re-normalisation of every key was ~20 % of the kernel's instructions.
+template <int DP, int KB, int ISSUER = 0, int PRENORM = 0>
 __global__ void __launch_bounds__(kThreads + 32 * ISSUER, KB == 32 ? (ISSUER ? 6 : 8) : (DP <= 32 ? 4 : 3))
     window_attention_tc_kernel(const Params p) {
   constexpr int kBlockKeys = KB;
@@ -113,7 +115,12 @@ __global__ void __launch_bounds__(kThreads + 32 * ISSUER, KB == 32 ? (ISSUER ? 6
     qlen = seg.y;
     qrow = __ldg(p.order + qp);
   }
-  if (!issuer) {
+  if (!issuer && PRENORM) {
+    const uint4 *src = reinterpret_cast<const uint4 *>(p.q + (int64_t)qrow * p.ld + h * DP);
+#pragma unroll
+    for (int c = 0; c < kChunks; ++c)
+      *reinterpret_cast<uint4 *>(q_s + core_off(tid, c, kSboQ)) = q_ok ? __ldg(src + c) : make_uint4(0, 0, 0, 0);
+  } else if (!issuer) {
     float f[DP];
     if (q_ok) {
       const uint4 *src = reinterpret_cast<const uint4 *>(p.q + (int64_t)qrow * p.ld + h * DP);
@@ -223,7 +230,13 @@ __global__ void __launch_bounds__(kThreads + 32 * ISSUER, KB == 32 ? (ISSUER ? 6
       tc_fence_after();
     }
     // ---- registers -> shared memory: K normalised (K-major), V transposed ----
-    if (key < kBlockKeys) {
+    if (PRENORM && key < kBlockKeys) {
+#pragma unroll
+      for (int c = 0; c < kChunks; ++c) {
+        if ((c & 1) != half) continue;
+        *reinterpret_cast<uint4 *>(k_s + core_off(key, c, kSboQ)) = k_ok_next ? k_raw[c] : make_uint4(0, 0, 0, 0);
+      }
+    } else if (key < kBlockKeys) {
       float f[DP];
       float ss = 0.0f;
 #pragma unroll
@@ -251,6 +264,8 @@ __global__ void __launch_bounds__(kThreads + 32 * ISSUER, KB == 32 ? (ISSUER ? 6
         }
         *reinterpret_cast<uint4 *>(k_s + core_off(key, c, kSboQ)) = make_uint4(w[0], w[1], w[2], w[3]);
       }
+    }
+    if (key < kBlockKeys) {
       // V is the B operand of O += P V with N = head dims, K = keys.  Its rows (keys) are stored as they come from
       // global memory -- 16-byte chunks of 8 dims -- in the MN-major no-swizzle core-matrix layout:
       //   element (dim n, key) -> (n / 8) * sbo + (key / 8) * lbo + (key % 8) * 16 + (n % 8) * 2
@@ -425,10 +440,9 @@ __global__ void __launch_bounds__(kThreads + 32 * ISSUER, KB == 32 ? (ISSUER ? 6
 
 using namespace os3d;
 
-extern "C" int os3d_window_attention_bf16_tc(const void *q, const void *k, const void *v, int64_t ld, int64_t ldv,
-                                             int64_t m, int heads, int dp, const int32_t *order, const int32_t *pos_seg,
-                                             const int32_t *level_info, const float *tau, float tau_min, void *out,
-                                             int64_t ldo, void *stream) {
+static int launch_attn_tc(const void *q, const void *k, const void *v, int64_t ld, int64_t ldv, int64_t m, int heads, int dp,
+                          const int32_t *order, const int32_t *pos_seg, const int32_t *level_info, const float *tau,
+                          float tau_min, void *out, int64_t ldo, void *stream, int prenorm) {
   if (m == 0) return 0;
   if (heads <= 0 || (dp != 16 && dp != 32 && dp != 48) || ld % 8 || ldv % 8 || ldo % 8) return OS3D_ERR_BAD_ARG;
   attn_tc::Params p;
@@ -447,10 +461,31 @@ extern "C" int os3d_window_attention_bf16_tc(const void *q, const void *k, const
   cudaStream_t st = (cudaStream_t)stream;
   const char *e = getenv("OS3D_ATTN_KB");                       // tuning override: keys per block for dp = 16
   const bool kb32 = e ? atoi(e) != 64 : true;
-  if (dp == 16 && kb32) attn_tc::window_attention_tc_kernel<16, 32><<<grid, attn_tc::kThreads, 0, st>>>(p);
-  else if (dp == 16) attn_tc::window_attention_tc_kernel<16, 64><<<grid, attn_tc::kThreads, 0, st>>>(p);
-  else if (dp == 32) attn_tc::window_attention_tc_kernel<32, 64><<<grid, attn_tc::kThreads, 0, st>>>(p);
-  else attn_tc::window_attention_tc_kernel<48, 64><<<grid, attn_tc::kThreads, 0, st>>>(p);
+  if (prenorm) {
+    if (dp == 16 && kb32) attn_tc::window_attention_tc_kernel<16, 32, 0, 1><<<grid, attn_tc::kThreads, 0, st>>>(p);
+    else if (dp == 16) attn_tc::window_attention_tc_kernel<16, 64, 0, 1><<<grid, attn_tc::kThreads, 0, st>>>(p);
+    else if (dp == 32) attn_tc::window_attention_tc_kernel<32, 64, 0, 1><<<grid, attn_tc::kThreads, 0, st>>>(p);
+    else attn_tc::window_attention_tc_kernel<48, 64, 0, 1><<<grid, attn_tc::kThreads, 0, st>>>(p);
+  } else {
+    if (dp == 16 && kb32) attn_tc::window_attention_tc_kernel<16, 32><<<grid, attn_tc::kThreads, 0, st>>>(p);
+    else if (dp == 16) attn_tc::window_attention_tc_kernel<16, 64><<<grid, attn_tc::kThreads, 0, st>>>(p);
+    else if (dp == 32) attn_tc::window_attention_tc_kernel<32, 64><<<grid, attn_tc::kThreads, 0, st>>>(p);
+    else attn_tc::window_attention_tc_kernel<48, 64><<<grid, attn_tc::kThreads, 0, st>>>(p);
+  }
   OS3D_LAUNCH_CHECK();
   return 0;
+}
+
+extern "C" int os3d_window_attention_bf16_tc(const void *q, const void *k, const void *v, int64_t ld, int64_t ldv,
+                                             int64_t m, int heads, int dp, const int32_t *order, const int32_t *pos_seg,
+                                             const int32_t *level_info, const float *tau, float tau_min, void *out,
+                                             int64_t ldo, void *stream) {
+  return launch_attn_tc(q, k, v, ld, ldv, m, heads, dp, order, pos_seg, level_info, tau, tau_min, out, ldo, stream, 0);
+}
+
+extern "C" int os3d_window_attention_bf16_tc_prenorm(const void *q, const void *k, const void *v, int64_t ld, int64_t ldv,
+                                                     int64_t m, int heads, int dp, const int32_t *order,
+                                                     const int32_t *pos_seg, const int32_t *level_info, const float *tau,
+                                                     float tau_min, void *out, int64_t ldo, void *stream) {
+  return launch_attn_tc(q, k, v, ld, ldv, m, heads, dp, order, pos_seg, level_info, tau, tau_min, out, ldo, stream, 1);
 }

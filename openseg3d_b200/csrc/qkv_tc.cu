@@ -349,8 +349,9 @@ static bool plan(int k, int n, int n_norm, int dp, int *nc_out, int *a_bufs_out,
     return false;
   const int ncb = (int)cdiv(k, kBlockK);
   const int budget = 227 * 1024 - 2048;
-  for (int a_bufs = 2; a_bufs >= 1; --a_bufs) {
-    for (int nc = 128 / dp * dp; nc >= dp; nc -= dp) {
+  // widest chunk first (more heads per chunk = more of the 16 epilogue warps busy, fewer hand-offs), then two x buffers
+  for (int nc = 128 / dp * dp; nc >= dp; nc -= dp) {
+    for (int a_bufs = 2; a_bufs >= 1; --a_bufs) {
       if (n % nc || n_norm % nc || n / nc > kMaxChunks) continue;
       const int stage_bytes = nc % 64 == 0 ? (nc / 64) * kSlotBytes : ((kTileM * (nc * 2 + 16) + 1023) & ~1023);
       const int bytes = a_bufs * ncb * kSlotBytes + 2 * ncb * nc * 128 + 2 * stage_bytes + 16 * 8 + 64 + n * 4;

@@ -596,7 +596,9 @@ static int launch_tc(tc::Params &p, cudaStream_t stream) {
   // (barrier round trips, proxy fence, issue), so two or three co-resident CTAs beat one CTA with a deep ring
   // (measured sweep: gpurun_out/sweep_cfg.log).  Per CTA: T accumulators (T * Cout <= 512 / ctas TMEM
   // columns), a weight ring of sb slabs and an A ring of sa (power of two) 16 KB slots within 227 KB / ctas.
-  const int ctas = cout <= 256 ? 2 : 1;
+  int ctas = cout <= 256 ? 2 : 1;
+  { const char *e = getenv("OS3D_SPCONV_CTAS");   // tuning override: co-resident CTAs per SM the geometry is sized for
+    if (e && (atoi(e) == 1 || (atoi(e) == 2 && cout <= 256))) ctas = atoi(e); }
   int tiles = (512 / ctas) / cout;
   tiles = tiles > 5 ? 5 : tiles < 1 ? 1 : tiles;
   while (tiles > 1 && cdiv(p.n_tiles, tiles) < 2 * 148 * ctas) --tiles;

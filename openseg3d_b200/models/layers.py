@@ -15,6 +15,7 @@ import numpy as np
 import torch
 import torch.nn as nn
 import torch.nn.functional as F
+import torch.utils.checkpoint
 
 from .. import _lib
 from .._lib import WindowCfg
@@ -455,7 +456,11 @@ class CosineMultiheadAttention(nn.MultiheadAttention):
         o_c = self._out_proj_chunks()
         hd = self.num_heads * dp
         use_v2 = _ATTN_IMPL == 'v2' and self._fixed_max_ok() and (self.num_heads * dp) % (96 if dp == 48 else 128) == 0
-        proj = self._qkv_proj(pos_dict, use_v2) if isinstance(pos_dict, PosDict) else None
+        # q, k are L2-normalised in the projection's epilogue (free there) for head widths up to 32; a 48-wide head would
+        # leave three of the four epilogue warps of a TMEM lane quarter idle (measured 0.53 vs 0.26 ms at level 4), so
+        # level 4 keeps the normalisation in the attention kernel's gather unless the v2 kernel needs it
+        prenorm = dp <= 32 or use_v2
+        proj = self._qkv_proj(pos_dict, prenorm) if isinstance(pos_dict, PosDict) else None
         if proj is not None:
             # ONE kernel: q | k | v = x [W_q | W_k | W_v]^T with the position term as a table row ((x + pos) W^T =
             # x W^T + (pos W^T)[pos_idx], biases folded in), head-padded layout; q, k L2-normalised in its epilogue when
@@ -464,7 +469,7 @@ class CosineMultiheadAttention(nn.MultiheadAttention):
             qkv = lin(feat, table=table, tab_idx=pos_dict.pos_idx)                           # [M, 3*H*dp]: q | k | v
             q_ptr, ld, ldv = qkv, 3 * hd, 3 * hd
             k_ptr, v_ptr = _lib._Raw(qkv.data_ptr() + hd * 2), _lib._Raw(qkv.data_ptr() + 2 * hd * 2)
-            normalized = use_v2
+            normalized = prenorm
         else:
             qk = F.linear(pos_dict.add_to(feat) if pos_dict is not None else feat, w_qk, b_qk)   # [M, 2*H*dp]: q | k
             v_ptr = F.linear(feat, w_v, b_v)                                                      # [M, H*dp]
@@ -481,8 +486,9 @@ class CosineMultiheadAttention(nn.MultiheadAttention):
             _lib.call('os3d_window_attention_bf16_v2', q_ptr, k_ptr, v_ptr, ld, ldv, m, self.num_heads, dp, seg.order,
                       seg.pos_seg, seg.level_info, tau, float(self.tau_min), out, hd, work=work)
         else:
-            _lib.call('os3d_window_attention_bf16_tc', q_ptr, k_ptr, v_ptr, ld, ldv, m, self.num_heads, dp,
-                      seg.order, seg.pos_seg, seg.level_info, tau, float(self.tau_min), out, hd, work=work)
+            _lib.call('os3d_window_attention_bf16_tc_prenorm' if normalized else 'os3d_window_attention_bf16_tc', q_ptr, k_ptr,
+                      v_ptr, ld, ldv, m, self.num_heads, dp, seg.order, seg.pos_seg, seg.level_info, tau,
+                      float(self.tau_min), out, hd, work=work)
         return out, o_c
 
     def _qkv_proj(self, pos_dict, normalize=False):
@@ -814,11 +820,18 @@ class SWFormerBlock(nn.Module):
                          drop_path=drop_path[i] if isinstance(drop_path, list) else drop_path) for i in range(depth)])
 
     def forward(self, batch_dict, using_checkpoint=True):
+        """Training with ``using_checkpoint`` (the reference's default, point_transformer_layer.py:321-323): every encoder
+        layer runs under torch.utils.checkpoint -- only its input is kept, the layer is recomputed in the backward (the
+        attention dropout mask is regenerated from its saved seed, torch's RNG state is restored for DropPath)."""
         x = batch_dict['voxel_features']
+        ckpt = using_checkpoint and self.training and torch.is_grad_enabled()
         for i, layer in enumerate(self.layers):
             s = 0 if i < int(self.depth / 2) else 1
-            x = layer(x, batch_dict[f'pos_dict_shift{s}'], batch_dict[f'flat2win_inds_shift{s}'],
-                      batch_dict[f'key_mask_shift{s}'])
+            args = (batch_dict[f'pos_dict_shift{s}'], batch_dict[f'flat2win_inds_shift{s}'], batch_dict[f'key_mask_shift{s}'])
+            if ckpt and x.requires_grad:
+                x = torch.utils.checkpoint.checkpoint(layer, x, *args, use_reentrant=False)
+            else:
+                x = layer(x, *args)
         return x
 
 

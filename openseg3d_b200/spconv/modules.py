@@ -158,16 +158,35 @@ class _SparseConvFunction(torch.autograd.Function):
             if pad:
                 gin = gin[:, :cin].contiguous()
         if ctx.needs_input_grad[1]:
-            gw = torch.empty((cout, 27, cin), dtype=torch.float32, device=weight.device)
-            g_t = gout.t().contiguous()
-            x_pad = torch.cat([features.detach(), features.new_zeros(1, cin)])      # row m_in = "no neighbour" -> zeros
-            idx_all = torch.where(ctx.nbr < 0, x_pad.shape[0] - 1, ctx.nbr).t().contiguous()     # [27, m_out]
+            # dW[:, k, :] = sum over the PAIRS of offset k of dout[out row]^T in[in row]: only rows that have a neighbour at
+            # offset k enter the product (6-17 of 27 offsets per row on lidar frames), from a pair list built once per
+            # kernel map (one host read of the 27 pair counts) and shared by every conv that uses the map
+            out_rows, in_rows, bounds = _pair_lists(ctx.nbr)
+            gw = torch.zeros((cout, 27, cin), dtype=torch.float32, device=weight.device)
+            x = features.detach()
             for k in range(27):
-                gw[:, k, :] = torch.mm(g_t, x_pad.index_select(0, idx_all[k])).float()
+                lo, hi = bounds[k], bounds[k + 1]
+                if hi > lo:
+                    gw[:, k, :] = torch.mm(gout.index_select(0, out_rows[lo:hi]).t(), x.index_select(0, in_rows[lo:hi])).float()
             gw = gw.reshape(weight.shape).to(weight.dtype)
         if ctx.has_bias and ctx.needs_input_grad[2]:
             gb = gout.float().sum(dim=0)
         return gin, gw, gb, None, None, None, None, None
+
+
+def _pair_lists(nbr):
+    """(output rows, input rows, bounds[28]) of a kernel map's pairs grouped by offset (offset-major, ascending output
+    row inside an offset) -- the per-offset pair lists spconv calls indice pairs; cached on the map tensor."""
+    hit = getattr(nbr, '_os3d_pairs_by_offset', None)
+    if hit is None:
+        nt = nbr.t()                                              # [27, m_out]
+        kk, rr = torch.nonzero(nt >= 0, as_tuple=True)            # sorted by offset, then output row
+        counts = torch.bincount(kk, minlength=27).tolist()        # one host read per kernel map
+        bounds = [0]
+        for c in counts:
+            bounds.append(bounds[-1] + int(c))
+        hit = nbr._os3d_pairs_by_offset = (rr.contiguous(), nt[kk, rr].long().contiguous(), bounds)
+    return hit
 
 
 class _PackedWeights(object):

@@ -34,7 +34,7 @@ def main():
         table = torch.randn(800, 2 * hd, device='cuda').bfloat16()
         ptab = torch.randn(800, c, device='cuda').bfloat16()
         idx = torch.randint(0, 800, (m,), device='cuda', dtype=torch.int32)
-        lin = WideLinear(w, bias, 16, n_norm=2 * hd, normalize=False)
+        lin = WideLinear(w, bias, dp, n_norm=2 * hd, normalize=True)
         wq, wv = w[:2 * hd].bfloat16().contiguous(), w[2 * hd:].bfloat16().contiguous()
         bq, bv = bias[:2 * hd].bfloat16(), bias[2 * hd:].bfloat16()
         xp = torch.empty_like(x)
