@@ -47,6 +47,24 @@ __device__ __forceinline__ float ex2_ftz(float x) {
   return y;
 }
 
+// packed pairs of floats for the two-wide FP32 instructions of sm_100 (FFMA2 / FADD2)
+__device__ __forceinline__ uint64_t pack2(float lo, float hi) {
+  uint64_t r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ void unpack2(uint64_t v, float &lo, float &hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
+__device__ __forceinline__ uint64_t ffma2(uint64_t a, uint64_t b, uint64_t c) {
+  uint64_t r;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+  return r;
+}
+__device__ __forceinline__ uint64_t fadd2(uint64_t a, uint64_t b) {
+  uint64_t r;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+
 // smem offset of element chunk (row r, 16-byte K-chunk c) in the K-major no-swizzle layout with 8-row group stride sbo
 __device__ __forceinline__ uint32_t core_off(int r, int c, int sbo) { return (r >> 3) * sbo + c * kLbo + (r & 7) * 16; }
 
@@ -215,7 +233,8 @@ __global__ void __launch_bounds__(kThreads + 32 * ISSUER, KB == 32 ? (ISSUER ? 6
       const uint4 *ksrc = reinterpret_cast<const uint4 *>(p.k + (int64_t)krow * p.ld + h * DP);
       const uint4 *vsrc = reinterpret_cast<const uint4 *>(p.v + (int64_t)krow * p.ldv + h * DP);
 #pragma unroll
-      for (int c = 0; c < kChunks; ++c) k_raw[c] = __ldg(ksrc + c);
+      for (int c = 0; c < kChunks; ++c)
+        if (!PRENORM || (c & 1) == half) k_raw[c] = __ldg(ksrc + c);      // PRENORM: only the chunks this thread stores
 #pragma unroll
       for (int c = 0; c < kVChunks; ++c)
         if (2 * c + half < kChunks) v_raw[c] = __ldg(vsrc + 2 * c + half);
@@ -355,14 +374,22 @@ __global__ void __launch_bounds__(kThreads + 32 * ISSUER, KB == 32 ? (ISSUER ? 6
       alpha = ex2_ftz((m_run - m_use) * scale);        // m_run = -inf -> 0 (l_run, O are still 0 then)
       neg_ms = -m_use * scale;
     }
-    float l_blk = 0.0f;
+    // two scores per instruction: FFMA2 / FADD2 (fma.rn.f32x2, add.rn.f32x2 -- the kernel is bound by its instruction
+    // count, not by latency: 65 % of the issue slots were busy)
+    const uint64_t sc2 = pack2(scale, scale), ng2 = pack2(neg_ms, neg_ms);
+    uint64_t l2 = pack2(0.0f, 0.0f);
 #pragma unroll
     for (int j = 0; j < kBlockKeys; j += 2) {
-      const float a = ex2_ftz(fmaf(s[j], scale, neg_ms)), b = ex2_ftz(fmaf(s[j + 1], scale, neg_ms));
-      l_blk += a + b;
+      float x0, x1;
+      unpack2(ffma2(pack2(s[j], s[j + 1]), sc2, ng2), x0, x1);
+      const float a = ex2_ftz(x0), b = ex2_ftz(x1);
+      l2 = fadd2(l2, pack2(a, b));
       const __nv_bfloat162 hh = __floats2bfloat162_rn(a, b);
       pk[j >> 1] = *reinterpret_cast<const uint32_t *>(&hh);
     }
+    float l_lo, l_hi;
+    unpack2(l2, l_lo, l_hi);
+    const float l_blk = l_lo + l_hi;
     l_run = l_run * alpha + l_blk;
     m_run = m_new;
     } else {
@@ -462,6 +489,7 @@ static int launch_attn_tc(const void *q, const void *k, const void *v, int64_t l
   const char *e = getenv("OS3D_ATTN_KB");                       // tuning override: keys per block for dp = 16
   const bool kb32 = e ? atoi(e) != 64 : true;
   if (prenorm) {
+    // (32 keys per block was also measured for dp = 32: 0.95 ms against 0.69 ms per level-3 layer with 64)
     if (dp == 16 && kb32) attn_tc::window_attention_tc_kernel<16, 32, 0, 1><<<grid, attn_tc::kThreads, 0, st>>>(p);
     else if (dp == 16) attn_tc::window_attention_tc_kernel<16, 64, 0, 1><<<grid, attn_tc::kThreads, 0, st>>>(p);
     else if (dp == 32) attn_tc::window_attention_tc_kernel<32, 64, 0, 1><<<grid, attn_tc::kThreads, 0, st>>>(p);

@@ -54,9 +54,9 @@ def main():
                 by = {}
                 for name, e0, e1, w in prof:
                     by[name] = by.get(name, 0.0) + e0.elapsed_time(e1) / reps
-                k = 'os3d_window_attention_bf16_' + ('tc' if impl == 'v1' else 'v2')
-                line.append(f'{impl}: attn {by.get(k, 0.0):.3f} ms ({flops / 1e9 / max(by.get(k, 1e-9), 1e-9):.0f} TFLOP/s useful)'
-                            + (f' + normalize {by.get("os3d_qk_normalize", 0.0):.3f}' if impl == 'v2' else ''))
+                t_k = sum(v for n, v in by.items() if n.startswith('os3d_window_attention_bf16_' + ('tc' if impl == 'v1' else 'v2')))
+                line.append(f'{impl}: attn {t_k:.3f} ms ({flops / 1e9 / max(t_k, 1e-9):.0f} TFLOP/s useful)'
+                            + f' proj {by.get("os3d_wide_linear_bf16", 0.0):.3f}')
             diff = (outs['v1'] - outs['v2']).abs().max().item() / outs['v1'].abs().max().item()
             print(f'L{level} shift{shift} tokens {m} windows {n_win} (mean {float(lens.mean()):.1f}, max {int(lens.max())}) C={c} '
                   f'useful {flops / 1e9:.1f} GFLOP | ' + ' | '.join(line) + f' | max rel diff v1-v2 {diff:.2e}', flush=True)
