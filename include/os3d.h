@@ -66,9 +66,10 @@ int os3d_scatter_max_f32(const float *feats, const int64_t *ids, int64_t n, int 
                          void *stream);
 int os3d_scatter_mean_f32(const float *feats, const int64_t *ids, int64_t n, int c, float *out, int32_t *counts,
                           const int32_t *counts_in, int64_t m, void *stream);
-/* argmax-free backward of scatter_max: grad_in[i] = grad_out[ids[i]] * (feats[i] == out[ids[i]]);  mean: /count */
+/* backward of scatter_max, torch_scatter semantics: the gradient of out[v, c] goes to ONE argmax row (the lowest point
+ * index among ties); arg: int32 [m * c] scratch.  mean: grad / count. */
 int os3d_scatter_max_bwd_f32(const float *grad_out, const float *feats, const float *out, const int64_t *ids, int64_t n,
-                             int c, int64_t m, float *grad_in, void *stream);
+                             int c, int64_t m, int32_t *arg, float *grad_in, void *stream);
 int os3d_scatter_mean_bwd_f32(const float *grad_out, const int64_t *ids, const int32_t *counts, int64_t n, int c,
                               int64_t m, float *grad_in, void *stream);
 

@@ -38,7 +38,7 @@ SIGNATURES = {
     'os3d_cart2polar_rows': [PTR, I64, I32, I32, PTR, PTR],
     'os3d_scatter_max_f32': [PTR, PTR, I64, I32, PTR, I64, I32, PTR],
     'os3d_scatter_mean_f32': [PTR, PTR, I64, I32, PTR, PTR, PTR, I64, PTR],
-    'os3d_scatter_max_bwd_f32': [PTR, PTR, PTR, PTR, I64, I32, I64, PTR, PTR],
+    'os3d_scatter_max_bwd_f32': [PTR, PTR, PTR, PTR, I64, I32, I64, PTR, PTR, PTR],
     'os3d_scatter_mean_bwd_f32': [PTR, PTR, PTR, I64, I32, I64, PTR, PTR],
     'os3d_gather_rows': [PTR, PTR, I64, I32, I32, PTR, PTR],
     'os3d_scatter_add_rows_f32': [PTR, PTR, I64, I32, PTR, I64, PTR],
@@ -127,7 +127,7 @@ def stream():
 # CUDA kernels launched by each entry point (memsets not counted) -- bench.py's gpu_launches evidence
 KERNELS_PER_CALL = {
     'os3d_voxelize': 5, 'os3d_cart2polar_rows': 1, 'os3d_scatter_max_f32': 2, 'os3d_scatter_mean_f32': 2,
-    'os3d_scatter_max_bwd_f32': 1, 'os3d_scatter_mean_bwd_f32': 1, 'os3d_gather_rows': 1, 'os3d_scatter_add_rows_f32': 1,
+    'os3d_scatter_max_bwd_f32': 2, 'os3d_scatter_mean_bwd_f32': 1, 'os3d_gather_rows': 1, 'os3d_scatter_add_rows_f32': 1,
     'os3d_hash_build': 1, 'os3d_subm_table': 1, 'os3d_strided_sites': 4, 'os3d_strided_tables': 2,
     'os3d_spconv_fwd_f32': 1, 'os3d_spconv_fwd_bf16': 1, 'os3d_spconv_fwd_bf16_ld': 1, 'os3d_pack_weight_f32': 1, 'os3d_pack_weight_bf16': 1, 'os3d_kernel_map_tiles': 1, 'os3d_kernel_map_order': 2, 'os3d_linear_bf16': 1, 'os3d_linear_tc_bf16': 1, 'os3d_pack_linear_bf16': 1, 'os3d_mlp_chain_bf16': 1, 'os3d_swformer_mlp_bf16': 1,
     'os3d_window_partition': 7, 'os3d_group_partition': 7, 'os3d_pos_embed': 1, 'os3d_qk_normalize': 1,

@@ -117,16 +117,30 @@ __global__ void mean_normalize_kernel(float *__restrict__ out, const int32_t *__
   out[t] = out[t] / (float)max(cnt, 1);
 }
 
-__global__ void scatter_max_bwd_kernel(const float *__restrict__ grad_out, const float *__restrict__ feats,
-                                       const float *__restrict__ out, const int64_t *__restrict__ ids, int64_t n,
-                                       int c, int64_t m, float *__restrict__ grad_in) {
+// Backward of scatter_max with torch_scatter's semantics: the gradient of out[v, c] goes to ONE argmax row.  Ties are not
+// exotic (bf16-rounded features, duplicated returns); among tied rows the lowest point index is taken (torch_scatter's
+// choice among ties is whichever thread wrote last -- any single tied row is a valid member).  Pass 1: arg[v, c] =
+// min{ i : feats[i, c] == out[v, c] } by atomicMin; pass 2 routes the gradient.
+__global__ void scatter_argmax_kernel(const float *__restrict__ feats, const float *__restrict__ out,
+                                      const int64_t *__restrict__ ids, int64_t n, int c, int64_t m, int32_t *__restrict__ arg) {
+  const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= n * c) return;
+  const int64_t row = t / c;
+  const int col = (int)(t - row * c);
+  const int64_t id = __ldg(ids + row);
+  if (id >= 0 && id < m && feats[t] == out[id * c + col]) atomicMin(arg + id * c + col, (int32_t)row);
+}
+
+__global__ void scatter_max_bwd_kernel(const float *__restrict__ grad_out, const int32_t *__restrict__ arg,
+                                       const int64_t *__restrict__ ids, int64_t n, int c, int64_t m,
+                                       float *__restrict__ grad_in) {
   const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= n * c) return;
   const int64_t row = t / c;
   const int col = (int)(t - row * c);
   const int64_t id = __ldg(ids + row);
   float g = 0.0f;
-  if (id >= 0 && id < m && feats[t] == out[id * c + col]) g = grad_out[id * c + col];
+  if (id >= 0 && id < m && __ldg(arg + id * c + col) == (int32_t)row) g = grad_out[id * c + col];
   grad_in[t] = g;
 }
 
@@ -204,10 +218,13 @@ extern "C" int os3d_scatter_mean_f32(const float *feats, const int64_t *ids, int
 }
 
 extern "C" int os3d_scatter_max_bwd_f32(const float *grad_out, const float *feats, const float *out, const int64_t *ids,
-                                        int64_t n, int c, int64_t m, float *grad_in, void *stream) {
+                                        int64_t n, int c, int64_t m, int32_t *arg, float *grad_in, void *stream) {
   if (n == 0) return 0;
-  scatter_max_bwd_kernel<<<grid_for(n * c, 256), 256, 0, (cudaStream_t)stream>>>(grad_out, feats, out, ids, n, c, m,
-                                                                                  grad_in);
+  if (n > 0x7fffffff || !arg) return OS3D_ERR_BAD_ARG;
+  cudaStream_t st = (cudaStream_t)stream;
+  OS3D_CUDA(cudaMemsetAsync(arg, 0x7f, sizeof(int32_t) * (size_t)m * c, st));        // 0x7f7f7f7f > any row index
+  scatter_argmax_kernel<<<grid_for(n * c, 256), 256, 0, st>>>(feats, out, ids, n, c, m, arg);
+  scatter_max_bwd_kernel<<<grid_for(n * c, 256), 256, 0, st>>>(grad_out, arg, ids, n, c, m, grad_in);
   OS3D_LAUNCH_CHECK();
   return 0;
 }

@@ -32,7 +32,8 @@ class _ScatterMax(Function):
     def backward(ctx, g):
         f, i, out = ctx.saved_tensors
         gi = torch.empty_like(f)
-        _lib.call('os3d_scatter_max_bwd_f32', g.float().contiguous(), f, out, i, f.shape[0], f.shape[1], out.shape[0], gi)
+        arg = torch.empty(out.shape, dtype=torch.int32, device=f.device)          # argmax row per (voxel, channel)
+        _lib.call('os3d_scatter_max_bwd_f32', g.float().contiguous(), f, out, i, f.shape[0], f.shape[1], out.shape[0], arg, gi)
         return gi.to(ctx.in_dtype), None, None, None
 
 

@@ -150,3 +150,29 @@ def test_voxel_to_point_matches_reference_golden(golden_dir):
     assert torch.equal(out.cpu(), torch.from_numpy(g['out']))
     bf = voxel_to_point(torch.from_numpy(g['feats']).cuda().bfloat16(), torch.from_numpy(g['ids']).cuda())
     assert torch.equal(bf.cpu(), torch.from_numpy(g['out']).bfloat16())
+
+
+def test_scatter_max_backward_with_ties_routes_to_one_row():
+    """torch_scatter semantics (VFE: vfe.py:24-25): among tied maxima ONE row receives the gradient (here the lowest
+    point index), so the input gradient of every (voxel, channel) sums to the output gradient -- ties must not multiply it."""
+    from openseg3d_b200.ops import scatter_max
+    torch.manual_seed(2)
+    n, m, c = 4000, 300, 8
+    feats = torch.randn(n, c).bfloat16().float()                       # 8-bit mantissa: many collisions
+    feats[::3] = feats[1::3][:feats[::3].shape[0]]                     # and exact duplicates
+    ids = torch.randint(0, m, (n,))
+    a = feats.clone().cuda().requires_grad_(True)
+    out = scatter_max(a, ids.cuda(), m)
+    w = torch.randn_like(out)
+    (out * w).sum().backward()
+    g = a.grad.cpu()
+    # per (voxel, channel): exactly one non-zero entry, equal to w, sitting on the first row that attains the maximum
+    tot = torch.zeros(m, c).index_add_(0, ids, g)
+    seen = torch.zeros(m, dtype=torch.bool).index_fill_(0, ids, True)
+    torch.testing.assert_close(tot[seen], w.cpu()[seen])
+    ref_out = torch.full((m, c), -float('inf')).scatter_reduce(0, ids[:, None].expand(-1, c), feats, 'amax')
+    is_max = feats == ref_out[ids]
+    first = torch.full((m, c), n, dtype=torch.long).scatter_reduce(0, ids[:, None].expand(-1, c),
+                                                                   torch.where(is_max, torch.arange(n)[:, None].expand(-1, c), n), 'amin')
+    expect = torch.where(first[ids] == torch.arange(n)[:, None], w.cpu()[ids], torch.zeros(()))
+    torch.testing.assert_close(g, expect)
