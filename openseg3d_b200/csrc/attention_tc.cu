@@ -94,8 +94,8 @@ __global__ void __launch_bounds__(kThreads + 32 * ISSUER, KB == 32 ? (ISSUER ? 6
   constexpr int kPBytes = (kTileQ / 8) * kSboP;
 
   __shared__ __align__(128) uint8_t q_s[kQBytes];
-  __shared__ __align__(128) uint8_t k_s[kKBytes];
-  __shared__ __align__(128) uint8_t v_s[kVBytes];
+  __shared__ __align__(128) uint8_t k_s[kKBytes];         // (double-buffering K / V to move the MMA-2 wait behind the
+  __shared__ __align__(128) uint8_t v_s[kVBytes];         //  gather was measured: no gain at any level)
   __shared__ __align__(128) uint8_t p_s[kPBytes];
   __shared__ __align__(8) uint64_t bars[4];               // MMA 1 done, MMA 2 done, (ISSUER) k_ready, p_ready
   __shared__ uint32_t tmem_slot;
@@ -225,11 +225,19 @@ __global__ void __launch_bounds__(kThreads + 32 * ISSUER, KB == 32 ? (ISSUER ? 6
   constexpr int kVChunks = (kChunks + 1) / 2;
   uint4 k_raw[kChunks], v_raw[kVChunks];
   bool k_ok_next = false;
-  auto prefetch = [&](int blk) {
+  // the voxel row of this thread's key is requested TWO blocks ahead, the K / V slices one block ahead: the dependent pair
+  // (order -> row -> slice) was one L2 round trip too long for a one-block lookahead (ncu: long-scoreboard stalls on the
+  // slice address, and block-wide barrier stalls behind the gathering warps)
+  int32_t krow_ahead = -1;
+  auto fetch_row = [&](int blk) {
     const int kp = ks + blk * kBlockKeys + key;
-    k_ok_next = blk < n_blocks && kp < ke && key < kBlockKeys;
+    krow_ahead = (blk < n_blocks && kp < ke && key < kBlockKeys) ? __ldg(p.order + kp) : -1;
+  };
+  auto prefetch = [&](int blk) {
+    const int32_t krow = krow_ahead;                       // fetched by fetch_row(blk) one block earlier
+    k_ok_next = krow >= 0;
+    fetch_row(blk + 1);
     if (k_ok_next) {
-      const int32_t krow = __ldg(p.order + kp);
       const uint4 *ksrc = reinterpret_cast<const uint4 *>(p.k + (int64_t)krow * p.ld + h * DP);
       const uint4 *vsrc = reinterpret_cast<const uint4 *>(p.v + (int64_t)krow * p.ldv + h * DP);
 #pragma unroll
@@ -240,6 +248,7 @@ __global__ void __launch_bounds__(kThreads + 32 * ISSUER, KB == 32 ? (ISSUER ? 6
         if (2 * c + half < kChunks) v_raw[c] = __ldg(vsrc + 2 * c + half);
     }
   };
+  fetch_row(0);
   prefetch(0);
 
   for (int blk = 0; blk < n_blocks; ++blk) {

@@ -350,10 +350,13 @@ extern "C" int os3d_linear_tc_bf16(const void *x, int64_t m, int k, int n, const
   slots = slots > lin::kMaxSlots ? lin::kMaxSlots : slots;
   p.slots = slots;
   const int smem = 1024 + p.ncb * n * 128 + slots * lin::kSlotBytes + tail;
-  static bool configured = false;
-  if (!configured) {
+  // the opt-in to > 48 KB of dynamic shared memory is a per-device attribute: once per device, not once per process
+  static bool configured[64] = {false};
+  int cfg_dev = 0;
+  OS3D_CUDA(cudaGetDevice(&cfg_dev));
+  if (cfg_dev < 0 || cfg_dev >= 64 || !configured[cfg_dev]) {
     OS3D_CUDA(cudaFuncSetAttribute(lin::linear_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    configured = true;
+    if (cfg_dev >= 0 && cfg_dev < 64) configured[cfg_dev] = true;
   }
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);

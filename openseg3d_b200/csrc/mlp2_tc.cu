@@ -551,10 +551,13 @@ extern "C" int os3d_swformer_mlp_bf16(const void *x, int64_t m, int c, int h, co
   p.s1 = pl.s1; p.s2 = pl.s2;
   p.w1_bytes = pl.w1_bytes;
   p.w2_bytes = pl.w2_bytes;
-  static bool configured = false;
-  if (!configured) {
+  // the opt-in to > 48 KB of dynamic shared memory is a per-device attribute: once per device, not once per process
+  static bool configured[64] = {false};
+  int cfg_dev = 0;
+  OS3D_CUDA(cudaGetDevice(&cfg_dev));
+  if (cfg_dev < 0 || cfg_dev >= 64 || !configured[cfg_dev]) {
     OS3D_CUDA(cudaFuncSetAttribute(mlp2::swformer_mlp_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    configured = true;
+    if (cfg_dev >= 0 && cfg_dev < 64) configured[cfg_dev] = true;
   }
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);

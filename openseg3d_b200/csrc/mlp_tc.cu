@@ -566,10 +566,13 @@ extern "C" int os3d_mlp_chain_bf16(const void *x, int64_t m, int64_t ldx, const 
   p.tmem_cols = pl.tmem_cols;
   p.acc_stride = pl.acc_stride;
   p.w_bytes_total = pl.w_bytes;
-  static bool configured = false;
-  if (!configured) {
+  // the opt-in to > 48 KB of dynamic shared memory is a per-device attribute: once per device, not once per process
+  static bool configured[64] = {false};
+  int cfg_dev = 0;
+  OS3D_CUDA(cudaGetDevice(&cfg_dev));
+  if (cfg_dev < 0 || cfg_dev >= 64 || !configured[cfg_dev]) {
     OS3D_CUDA(cudaFuncSetAttribute(mlp::mlp_chain_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    configured = true;
+    if (cfg_dev >= 0 && cfg_dev < 64) configured[cfg_dev] = true;
   }
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);

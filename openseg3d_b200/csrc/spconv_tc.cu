@@ -623,10 +623,13 @@ static int launch_tc(tc::Params &p, cudaStream_t stream) {
   p.sa_log2 = sa_log2;
   p.sb = sb;
   const int smem = 1024 + sa * tc::kATileBytes + sb * b_bytes + tail;
-  static bool configured = false;
-  if (!configured) {
+  // the opt-in to > 48 KB of dynamic shared memory is a per-device attribute: once per device, not once per process
+  static bool configured[64] = {false};
+  int cfg_dev = 0;
+  OS3D_CUDA(cudaGetDevice(&cfg_dev));
+  if (cfg_dev < 0 || cfg_dev >= 64 || !configured[cfg_dev]) {
     OS3D_CUDA(cudaFuncSetAttribute(tc::spconv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    configured = true;
+    if (cfg_dev >= 0 && cfg_dev < 64) configured[cfg_dev] = true;
   }
   tc::spconv_tc_kernel<<<(unsigned)cdiv(p.n_tiles, tiles), tc::kThreads, smem, stream>>>(p);
   OS3D_LAUNCH_CHECK();
