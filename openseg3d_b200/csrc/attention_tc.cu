@@ -25,6 +25,9 @@ namespace os3d {
 namespace attn_tc {
 using namespace ptx;
 
+#ifndef OS3D_ATTN_CTAS
+#define OS3D_ATTN_CTAS 7
+#endif
 constexpr int kTileQ = 128;
 constexpr int kThreads = 128;
 constexpr int kLbo = 128;                 // bytes between core matrices along K
@@ -69,36 +72,45 @@ __device__ __forceinline__ uint64_t fadd2(uint64_t a, uint64_t b) {
 __device__ __forceinline__ uint32_t core_off(int r, int c, int sbo) { return (r >> 3) * sbo + c * kLbo + (r & 7) * 16; }
 
 // DP: padded head dim.  KB: keys per block.  TMEM: S in columns [0, KB), O in [KB, KB + DP) of a power-of-two allocation
-// -- with KB = 32 and DP = 16 that is 64 columns, so 8 CTAs share an SM (and short windows waste half as many masked
-// score columns); KB = 64 otherwise (128 columns, 4 CTAs).
+// -- with KB = 32 and DP = 16 that is 64 columns, so up to 8 CTAs share an SM (and short windows waste half as many
+// masked score columns); KB = 64 otherwise (128 columns, 4 CTAs).
 //
-// ISSUER = 1 (never instantiated: no launch path selects it, so it is not in the library; superseded by attention_v2.cu,
-// which is built around a dedicated issuer warp): a fifth warp does
-// nothing but issue the MMAs.  The four softmax warps then never execute a block-wide barrier in the key loop -- they
-// publish K / V (k_ready) and P (p_ready) with an mbarrier arrive and go on -- and warp 0 is no longer the straggler that
-// issues `UTCHMMA`s while the other three wait for it (ncu, ISSUER = 0: 24 % of the stall samples on those two barriers).
+// KB = 64: P never touches shared memory (kPT): each thread packs its row of probabilities to bf16 pairs and writes them with
+// tcgen05.st over the first KB / 2 columns of its own S row (which it holds in registers by then); MMA 2 takes its A
+// operand from tensor memory.  Warps whose rows see no key of a block write nothing at all: MMA 2 is issued with their
+// 32 lanes in the disable-output-lane mask (O is zeroed once up front, so every MMA 2 accumulates).  Before this the P
+// tile went through 16-byte shared-memory stores -- 60 % of the kernel's shared-memory wavefronts on an LSU pipe that ncu
+// showed 71-73 % busy (profiles/r02h_attention_l{1,3}_full.txt) -- including the all-zero rows of skipped warps.
+// Measured per layer: level 3 0.666 -> 0.625 ms, level 4 0.387 -> 0.370 ms.  With KB = 32 (dp = 16) the P row is only four
+// 16-byte stores and the tensor-memory round trip was slower (level 1 0.670 -> 0.704 ms), so that variant keeps P in
+// shared memory as the A operand of a descriptor MMA.
+//
 // PRENORM = 1: q and k arrive already L2-normalised per head (the in-projection kernel's epilogue, qkv_tc.cu): the gather
 // is a plain copy -- the per-(tile, head) re-normalisation of every key was ~20 % of the kernel's instructions.
-template <int DP, int KB, int ISSUER = 0, int PRENORM = 0>
-__global__ void __launch_bounds__(kThreads + 32 * ISSUER, KB == 32 ? (ISSUER ? 6 : 8) : (DP <= 32 ? 4 : 3))
+// (A variant with a fifth, MMA-issuing warp and mbarrier hand-offs was built and measured in round 1 and superseded by
+// attention_v2.cu in round 2; both lose to this block-synchronous kernel at 4-7 CTAs per SM: DESIGN.md 3.2.)
+template <int DP, int KB, int PRENORM = 0>
+__global__ void __launch_bounds__(kThreads, KB == 32 ? OS3D_ATTN_CTAS : (DP <= 32 ? 4 : 3))
     window_attention_tc_kernel(const Params p) {
   constexpr int kBlockKeys = KB;
   constexpr int kTmemCols = (KB + DP) <= 64 ? 64 : 128;
   constexpr int kChunks = DP / 8;                         // 16-byte chunks per head slice
   constexpr int kSboQ = kChunks * kLbo + 16;              // +16: stagger 8-row groups across banks
+  constexpr bool kPT = KB == 64;                          // P in tensor memory
   constexpr int kSboP = (kBlockKeys / 8) * kLbo + 16;
   constexpr int kSboV = (kBlockKeys / 8) * kLbo + 16;     // V as the MN-major B operand: stride between 8-dim groups; 8-key groups are kLbo apart
   constexpr int kQBytes = (kTileQ / 8) * kSboQ;
   constexpr int kKBytes = (kBlockKeys / 8) * kSboQ;
   constexpr int kVBytes = (DP / 8) * kSboV;
-  constexpr int kPBytes = (kTileQ / 8) * kSboP;
+  constexpr int kPBytes = kPT ? 16 : (kTileQ / 8) * kSboP;
 
   __shared__ __align__(128) uint8_t q_s[kQBytes];
   __shared__ __align__(128) uint8_t k_s[kKBytes];         // (double-buffering K / V to move the MMA-2 wait behind the
   __shared__ __align__(128) uint8_t v_s[kVBytes];         //  gather was measured: no gain at any level)
-  __shared__ __align__(128) uint8_t p_s[kPBytes];
-  __shared__ __align__(8) uint64_t bars[4];               // MMA 1 done, MMA 2 done, (ISSUER) k_ready, p_ready
+  __shared__ __align__(128) uint8_t p_s[kPBytes];         // !kPT only
+  __shared__ __align__(8) uint64_t bars[2];               // MMA 1 done, MMA 2 done
   __shared__ uint32_t tmem_slot;
+  __shared__ uint32_t lanes_off[4];                       // per warp: 0xffffffff when its rows sit out MMA 2 of this block
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   // heads of one query tile are adjacent in launch order: they run at the same time and share the q / k / v rows (each
@@ -111,20 +123,16 @@ __global__ void __launch_bounds__(kThreads + 32 * ISSUER, KB == 32 ? (ISSUER ? 6
   const int p_last = min(p0 + kTileQ, n_tok) - 1;
 
   const uint32_t bar1 = smem_u32(&bars[0]), bar2 = smem_u32(&bars[1]);
-  const uint32_t k_ready = smem_u32(&bars[2]), p_ready = smem_u32(&bars[3]);
   if (tid == 0) {
     mbar_init(bar1, 1);
     mbar_init(bar2, 1);
-    mbar_init(k_ready, 4);
-    mbar_init(p_ready, 4);
     fence_barrier_init();
   }
   if (warp == 0) tmem_alloc(smem_u32(&tmem_slot), kTmemCols);
 
   // ---- this thread's query row ----
-  const bool issuer = ISSUER && warp == 4;               // (warp-uniform) this warp only issues MMAs
   const int qp = p0 + tid;
-  const bool q_ok = !issuer && qp <= p_last;
+  const bool q_ok = qp <= p_last;
   int qws = 0, qlen = 0;                 // this row's window = grouped positions [qws, qws + qlen)
   int32_t qrow = 0;
   if (q_ok) {
@@ -133,12 +141,12 @@ __global__ void __launch_bounds__(kThreads + 32 * ISSUER, KB == 32 ? (ISSUER ? 6
     qlen = seg.y;
     qrow = __ldg(p.order + qp);
   }
-  if (!issuer && PRENORM) {
+  if (PRENORM) {
     const uint4 *src = reinterpret_cast<const uint4 *>(p.q + (int64_t)qrow * p.ld + h * DP);
 #pragma unroll
     for (int c = 0; c < kChunks; ++c)
       *reinterpret_cast<uint4 *>(q_s + core_off(tid, c, kSboQ)) = q_ok ? __ldg(src + c) : make_uint4(0, 0, 0, 0);
-  } else if (!issuer) {
+  } else {
     float f[DP];
     if (q_ok) {
       const uint4 *src = reinterpret_cast<const uint4 *>(p.q + (int64_t)qrow * p.ld + h * DP);
@@ -188,33 +196,16 @@ __global__ void __launch_bounds__(kThreads + 32 * ISSUER, KB == 32 ? (ISSUER ? 6
   const uint32_t idesc1 = make_idesc_bf16(kTileQ, kBlockKeys), idesc2 = make_idesc_bf16(kTileQ, DP) | (1u << 16);   // bit 16: B is MN-major
   const float scale = 1.4426950408889634f / fmaxf(__ldg(p.tau), p.tau_min);
   const bool fixed_max = scale <= 60.0f;
+  if constexpr (kPT) {
+    // O starts at zero: MMA 2 always accumulates (rows of warps that sit a block out are masked, not multiplied by 0)
+    uint32_t z[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) z[i] = 0u;
+#pragma unroll
+    for (int c0 = 0; c0 < DP; c0 += 16) tmem_st16(tmem_row + kBlockKeys + c0, z);
+    tmem_st_wait();
+  }
 
-  if (issuer) {
-    // ---- MMA issuer warp (ISSUER = 1): S = Q K^T when the four softmax warps have published K / V, O += P V when they
-    // have published P; descriptors are built once
-    const uint64_t qd = make_kmajor_nosw_desc(smem_u32(q_s), kLbo, kSboQ), kd = make_kmajor_nosw_desc(smem_u32(k_s), kLbo, kSboQ);
-    const uint64_t pd = make_kmajor_nosw_desc(smem_u32(p_s), kLbo, kSboP), vd = make_kmajor_nosw_desc(smem_u32(v_s), kLbo, kSboV);
-    constexpr uint64_t kStep = (uint64_t)(2 * kLbo) >> 4;       // one K = 16 step along the operand, in descriptor units
-    for (int blk = 0; blk < n_blocks; ++blk) {
-      mbar_wait(k_ready, (uint32_t)blk & 1u);
-      tc_fence_after();
-      if (elect_one()) {
-#pragma unroll
-        for (int s = 0; s < DP / 16; ++s) umma_bf16(tmem_base, qd + s * kStep, kd + s * kStep, idesc1, s > 0 ? 1u : 0u);
-        umma_commit(bar1);
-      }
-      __syncwarp();
-      mbar_wait(p_ready, (uint32_t)blk & 1u);
-      tc_fence_after();
-      if (elect_one()) {
-#pragma unroll
-        for (int s2 = 0; s2 < kBlockKeys / 16; ++s2)
-          umma_bf16(tmem_base + kBlockKeys, pd + s2 * kStep, vd + s2 * kStep, idesc2, (blk > 0 || s2 > 0) ? 1u : 0u);
-        umma_commit(bar2);
-      }
-      __syncwarp();
-    }
-  } else {
   float m_run = -INFINITY, l_run = 0.0f;
   uint32_t ph1 = 0, ph2 = 0;
 
@@ -252,7 +243,7 @@ __global__ void __launch_bounds__(kThreads + 32 * ISSUER, KB == 32 ? (ISSUER ? 6
   prefetch(0);
 
   for (int blk = 0; blk < n_blocks; ++blk) {
-    if (blk > 0) {            // MMA 2 of the previous block still reads V and P
+    if (blk > 0) {            // MMA 2 of the previous block still reads V (shared memory) and P (tensor memory, under S)
       mbar_wait(bar2, ph2);
       ph2 ^= 1;
       tc_fence_after();
@@ -309,10 +300,6 @@ __global__ void __launch_bounds__(kThreads + 32 * ISSUER, KB == 32 ? (ISSUER ? 6
     }
     fence_proxy_async();
     tc_fence_before();
-    if constexpr (ISSUER) {
-      __syncwarp();
-      if (lane == 0) mbar_arrive(k_ready);
-    } else {
     __syncthreads();
     if (tid == 0) {
       tc_fence_after();
@@ -321,7 +308,6 @@ __global__ void __launch_bounds__(kThreads + 32 * ISSUER, KB == 32 ? (ISSUER ? 6
         umma_bf16(tmem_base, make_kmajor_nosw_desc(smem_u32(q_s) + s * 2 * kLbo, kLbo, kSboQ),
                   make_kmajor_nosw_desc(smem_u32(k_s) + s * 2 * kLbo, kLbo, kSboQ), idesc1, s > 0 ? 1u : 0u);
       umma_commit(bar1);
-    }
     }
     prefetch(blk + 1);        // global loads for the next key block fly during MMA 1, the softmax and MMA 2
     mbar_wait(bar1, ph1);
@@ -337,12 +323,18 @@ __global__ void __launch_bounds__(kThreads + 32 * ISSUER, KB == 32 ? (ISSUER ? 6
     // are folded into one FFMA feeding ex2.approx.ftz (masked scores are -inf -> probability exactly 0)
     const uint64_t valid = hi > lo ? ((~0ull >> (64 - (hi - lo))) << lo) : 0ull;
     const uint32_t v_lo = (uint32_t)valid, v_hi = (uint32_t)(valid >> 32);
-    uint32_t pk[kBlockKeys / 2];
     float alpha = 1.0f;
+    uint32_t pk[kBlockKeys / 2];                            // the row of probabilities, packed bf16 pairs
     // Windows are short, so most (warp, key block) pairs are entirely off the block diagonal: one vote skips the TMEM
-    // load and the whole softmax for them (their P rows are zero).
+    // load, the whole softmax and the P store for them, and takes their rows out of MMA 2.
     const bool warp_has_keys = __any_sync(0xffffffffu, valid != 0ull);
+    if (kPT && lane == 0) lanes_off[warp] = warp_has_keys ? 0u : 0xffffffffu;
     if (warp_has_keys) {
+    // q and k are unit vectors, so a raw score never exceeds 1 (+ bf16 rounding): with a moderate temperature the
+    // softmax can use the FIXED reference maximum 1 -- no running maximum, no FMNMX per score, no rescaling of O --
+    // and cannot underflow (2 * scale <= 120 binades).  Small temperatures keep the online maximum.
+    const uint64_t full_mask = kBlockKeys == 64 ? ~0ull : ((1ull << (kBlockKeys & 63)) - 1ull);
+    const bool all_valid = __all_sync(0xffffffffu, valid == full_mask);
     float s[kBlockKeys];
     {
       uint32_t r[32];
@@ -357,11 +349,6 @@ __global__ void __launch_bounds__(kThreads + 32 * ISSUER, KB == 32 ? (ISSUER ? 6
         for (int i = 0; i < 32; ++i) s[32 + i] = __uint_as_float(r[i]);
       }
     }
-    // q and k are unit vectors, so a raw score never exceeds 1 (+ bf16 rounding): with a moderate temperature the
-    // softmax can use the FIXED reference maximum 1 -- no running maximum, no FMNMX per score, no rescaling of O --
-    // and cannot underflow (2 * scale <= 120 binades).  Small temperatures keep the online maximum.
-    const uint64_t full_mask = kBlockKeys == 64 ? ~0ull : ((1ull << (kBlockKeys & 63)) - 1ull);
-    const bool all_valid = __all_sync(0xffffffffu, valid == full_mask);
     float m_new = m_run, neg_ms;
     if (fixed_max) {
       if (!all_valid) {
@@ -384,30 +371,37 @@ __global__ void __launch_bounds__(kThreads + 32 * ISSUER, KB == 32 ? (ISSUER ? 6
       neg_ms = -m_use * scale;
     }
     // two scores per instruction: FFMA2 / FADD2 (fma.rn.f32x2, add.rn.f32x2 -- the kernel is bound by its instruction
-    // count, not by latency: 65 % of the issue slots were busy)
+    // count, not by latency: 65 % of the issue slots were busy).  Each group of 32 keys goes back to tensor memory as 16
+    // packed bf16 pairs (one tcgen05.st) as soon as it is done.
     const uint64_t sc2 = pack2(scale, scale), ng2 = pack2(neg_ms, neg_ms);
     uint64_t l2 = pack2(0.0f, 0.0f);
 #pragma unroll
-    for (int j = 0; j < kBlockKeys; j += 2) {
-      float x0, x1;
-      unpack2(ffma2(pack2(s[j], s[j + 1]), sc2, ng2), x0, x1);
-      const float a = ex2_ftz(x0), b = ex2_ftz(x1);
-      l2 = fadd2(l2, pack2(a, b));
-      const __nv_bfloat162 hh = __floats2bfloat162_rn(a, b);
-      pk[j >> 1] = *reinterpret_cast<const uint32_t *>(&hh);
+    for (int g = 0; g < kBlockKeys; g += 32) {
+#pragma unroll
+      for (int j = 0; j < 32; j += 2) {
+        float x0, x1;
+        unpack2(ffma2(pack2(s[g + j], s[g + j + 1]), sc2, ng2), x0, x1);
+        const float a = ex2_ftz(x0), b = ex2_ftz(x1);
+        l2 = fadd2(l2, pack2(a, b));
+        const __nv_bfloat162 hh = __floats2bfloat162_rn(a, b);
+        pk[(g + j) >> 1] = *reinterpret_cast<const uint32_t *>(&hh);
+      }
+      if constexpr (kPT) tmem_st16(tmem_row + g / 2, reinterpret_cast<const uint32_t (&)[16]>(pk[g / 2]));
     }
     float l_lo, l_hi;
     unpack2(l2, l_lo, l_hi);
     const float l_blk = l_lo + l_hi;
     l_run = l_run * alpha + l_blk;
     m_run = m_new;
-    } else {
+    } else if constexpr (!kPT) {
 #pragma unroll
       for (int i = 0; i < kBlockKeys / 2; ++i) pk[i] = 0u;
     }
+    if constexpr (!kPT) {
 #pragma unroll
-    for (int c = 0; c < kBlockKeys / 8; ++c)
-      *reinterpret_cast<uint4 *>(p_s + core_off(tid, c, kSboP)) = make_uint4(pk[4 * c], pk[4 * c + 1], pk[4 * c + 2], pk[4 * c + 3]);
+      for (int c = 0; c < kBlockKeys / 8; ++c)
+        *reinterpret_cast<uint4 *>(p_s + core_off(tid, c, kSboP)) = make_uint4(pk[4 * c], pk[4 * c + 1], pk[4 * c + 2], pk[4 * c + 3]);
+    }
     // rescale O if any row of this warp moved its maximum (tcgen05.ld / st are warp-collective)
     if (blk > 0 && __any_sync(0xffffffffu, alpha != 1.0f)) {
 #pragma unroll
@@ -419,16 +413,15 @@ __global__ void __launch_bounds__(kThreads + 32 * ISSUER, KB == 32 ? (ISSUER ? 6
         for (int i = 0; i < 16; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
         tmem_st16(tmem_row + kBlockKeys + c0, o);
       }
-      tmem_st_wait();
+      if constexpr (!kPT) tmem_st_wait();
     }
-    fence_proxy_async();
+    if constexpr (kPT) {
+      if (warp_has_keys) tmem_st_wait();
+    }
+    if constexpr (!kPT) fence_proxy_async();
     tc_fence_before();
-    if constexpr (ISSUER) {
-      __syncwarp();
-      if (lane == 0) mbar_arrive(p_ready);
-    } else {
     __syncthreads();
-    if (tid == 0) {
+    if (!kPT && tid == 0) {
       tc_fence_after();
 #pragma unroll
       for (int s2 = 0; s2 < kBlockKeys / 16; ++s2)
@@ -436,6 +429,17 @@ __global__ void __launch_bounds__(kThreads + 32 * ISSUER, KB == 32 ? (ISSUER ? 6
                   make_kmajor_nosw_desc(smem_u32(v_s) + s2 * 2 * kLbo, kLbo, kSboV), idesc2, (blk > 0 || s2 > 0) ? 1u : 0u);
       umma_commit(bar2);
     }
+    if (kPT && tid == 0) {
+      tc_fence_after();
+      const uint32_t off0 = lanes_off[0], off1 = lanes_off[1], off2 = lanes_off[2], off3 = lanes_off[3];
+      if ((off0 & off1 & off2 & off3) == 0u) {
+        const uint32_t v_hi_w = nosw_desc_hi(kSboV);
+#pragma unroll
+        for (int s2 = 0; s2 < kBlockKeys / 16; ++s2)
+          umma_bf16_ts_acc(tmem_base + kBlockKeys, tmem_base + s2 * 8, nosw_desc_lo(smem_u32(v_s) + s2 * 2 * kLbo, kLbo), v_hi_w,
+                           idesc2, off0, off1, off2, off3);
+      }
+      umma_commit(bar2);
     }
   }
 
@@ -462,7 +466,6 @@ __global__ void __launch_bounds__(kThreads + 32 * ISSUER, KB == 32 ? (ISSUER ? 6
       }
     }
   }
-  }   // !issuer
   tc_fence_before();
   __syncthreads();
   if (warp == 0) {
@@ -499,10 +502,10 @@ static int launch_attn_tc(const void *q, const void *k, const void *v, int64_t l
   const bool kb32 = e ? atoi(e) != 64 : true;
   if (prenorm) {
     // (32 keys per block was also measured for dp = 32: 0.95 ms against 0.69 ms per level-3 layer with 64)
-    if (dp == 16 && kb32) attn_tc::window_attention_tc_kernel<16, 32, 0, 1><<<grid, attn_tc::kThreads, 0, st>>>(p);
-    else if (dp == 16) attn_tc::window_attention_tc_kernel<16, 64, 0, 1><<<grid, attn_tc::kThreads, 0, st>>>(p);
-    else if (dp == 32) attn_tc::window_attention_tc_kernel<32, 64, 0, 1><<<grid, attn_tc::kThreads, 0, st>>>(p);
-    else attn_tc::window_attention_tc_kernel<48, 64, 0, 1><<<grid, attn_tc::kThreads, 0, st>>>(p);
+    if (dp == 16 && kb32) attn_tc::window_attention_tc_kernel<16, 32, 1><<<grid, attn_tc::kThreads, 0, st>>>(p);
+    else if (dp == 16) attn_tc::window_attention_tc_kernel<16, 64, 1><<<grid, attn_tc::kThreads, 0, st>>>(p);
+    else if (dp == 32) attn_tc::window_attention_tc_kernel<32, 64, 1><<<grid, attn_tc::kThreads, 0, st>>>(p);
+    else attn_tc::window_attention_tc_kernel<48, 64, 1><<<grid, attn_tc::kThreads, 0, st>>>(p);
   } else {
     if (dp == 16 && kb32) attn_tc::window_attention_tc_kernel<16, 32><<<grid, attn_tc::kThreads, 0, st>>>(p);
     else if (dp == 16) attn_tc::window_attention_tc_kernel<16, 64><<<grid, attn_tc::kThreads, 0, st>>>(p);

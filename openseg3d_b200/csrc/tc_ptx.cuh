@@ -108,6 +108,21 @@ __device__ __forceinline__ void umma_bf16_words(uint32_t tmem_d, uint32_t a_lo, 
       "}" ::"r"(tmem_d), "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accum)
       : "memory");
 }
+// A operand in TENSOR MEMORY (M = 128: row i = lane i, 16-bit elements packed two per 32-bit column, so one K = 16 step
+// is 8 columns), B through a shared-memory descriptor given as two words; always accumulates into D.  lane_off[w] is the
+// disable-output-lane mask of lanes [32 w, 32 w + 32): set bits leave those rows of D untouched.
+__device__ __forceinline__ void umma_bf16_ts_acc(uint32_t tmem_d, uint32_t tmem_a, uint32_t b_lo, uint32_t b_hi, uint32_t idesc,
+                                                 uint32_t off0, uint32_t off1, uint32_t off2, uint32_t off3) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      ".reg .b64 db;\n\t"
+      "mov.b64 db, {%2, %3};\n\t"
+      "setp.eq.b32 p, %4, %4;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], db, %4, {%5, %6, %7, %8}, p;\n\t"
+      "}" ::"r"(tmem_d), "r"(tmem_a), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(off0), "r"(off1), "r"(off2), "r"(off3)
+      : "memory");
+}
 // words of a no-swizzle (INTERLEAVE) descriptor
 __device__ __forceinline__ uint32_t nosw_desc_lo(uint32_t saddr, uint32_t lbo) { return ((saddr & 0x3ffffu) >> 4) | ((lbo >> 4) << 16); }
 __device__ __forceinline__ uint32_t nosw_desc_hi(uint32_t sbo) { return (sbo >> 4) | (1u << 14); }

@@ -1,6 +1,6 @@
 """Summarise an `ncu --metrics gpu__time_duration.sum[,dram__bytes_read.sum,dram__bytes_write.sum] --csv` launch list by
-kernel (used for profiles/*.txt).   python tools/summarize_launches.py launches.csv [top] [first_launch_id]
-first_launch_id: ignore launches with a smaller ncu ID (warm-up forwards)."""
+kernel (used for profiles/*.txt).   python tools/summarize_launches.py launches.csv [top] [first_launch_id] [end_launch_id]
+first_launch_id / end_launch_id: keep launches with first <= ncu ID < end (one forward out of several)."""
 import collections
 import csv
 import re
@@ -16,12 +16,12 @@ def to_mb(v, unit):
     return v / 1e6 if u == 'byte' else v / 1e3 if u.startswith('k') else v * 1e3 if u.startswith('g') else v
 
 
-def main(path, top=30, first_id=0):
+def main(path, top=30, first_id=0, end_id=1 << 60):
     lines = [l for l in open(path) if not l.startswith('==')]
     per = collections.defaultdict(dict)           # launch id -> {name, ms, rd, wr}
     for row in csv.DictReader(lines):
         i = int(row['ID'])
-        if i < first_id:
+        if i < first_id or i >= end_id:
             continue
         v = float(row['Metric Value'].replace(',', ''))
         d = per[i]
@@ -49,4 +49,5 @@ def main(path, top=30, first_id=0):
 
 
 if __name__ == '__main__':
-    main(sys.argv[1], int(sys.argv[2]) if len(sys.argv) > 2 else 30, int(sys.argv[3]) if len(sys.argv) > 3 else 0)
+    main(sys.argv[1], int(sys.argv[2]) if len(sys.argv) > 2 else 30, int(sys.argv[3]) if len(sys.argv) > 3 else 0,
+         int(sys.argv[4]) if len(sys.argv) > 4 else 1 << 60)
