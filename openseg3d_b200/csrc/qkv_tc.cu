@@ -28,6 +28,29 @@
 
 namespace os3d {
 namespace qkv {
+// packed pairs of floats for the two-wide FP32 instructions of sm_100 (FFMA2 / FADD2 / FMUL2)
+__device__ __forceinline__ uint64_t pack2(float lo, float hi) {
+  uint64_t r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ void unpack2(uint64_t v, float &lo, float &hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
+__device__ __forceinline__ uint64_t ffma2(uint64_t a, uint64_t b, uint64_t c) {
+  uint64_t r;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+  return r;
+}
+__device__ __forceinline__ uint64_t fadd2(uint64_t a, uint64_t b) {
+  uint64_t r;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+__device__ __forceinline__ uint64_t fmul2(uint64_t a, uint64_t b) {
+  uint64_t r;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+
 using namespace ptx;
 
 constexpr int kTileM = 128;
@@ -234,22 +257,30 @@ __global__ void __launch_bounds__(kThreads, 1) qkv_proj_tc_kernel(const __grid_c
                 const uint4 t4 = tcur[hi * kV + c];
                 const uint32_t tw[4] = {t4.x, t4.y, t4.z, t4.w};
 #pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                  y[c * 8 + 2 * i] += __uint_as_float(tw[i] << 16);
-                  y[c * 8 + 2 * i + 1] += __uint_as_float(tw[i] & 0xffff0000u);
-                }
+                for (int i = 0; i < 4; ++i)            // two-wide FP32 add (FADD2)
+                  unpack2(fadd2(pack2(y[c * 8 + 2 * i], y[c * 8 + 2 * i + 1]),
+                                pack2(__uint_as_float(tw[i] << 16), __uint_as_float(tw[i] & 0xffff0000u))),
+                          y[c * 8 + 2 * i], y[c * 8 + 2 * i + 1]);
               }
             } else if (p.bias) {
 #pragma unroll
               for (int i = 0; i < DP; ++i) y[i] += bias_s[gcol + i];
             }
             if (p.normalize) {
-              float ss = 0.0f;                           // F.normalize over the head (eps 1e-12), cosine_msa.py:152-153
+              // F.normalize over the head (eps 1e-12), cosine_msa.py:152-153: y / max(|y|, 1e-12) = y * rsqrt(max(|y|^2, 1e-24));
+              // FFMA2 / FMUL2 halve the per-element instruction count, rsqrt.approx replaces the IEEE sqrt + divide
+              uint64_t ss2 = pack2(0.0f, 0.0f);
 #pragma unroll
-              for (int i = 0; i < DP; ++i) ss = fmaf(y[i], y[i], ss);
-              const float inv = 1.0f / fmaxf(sqrtf(ss), 1e-12f);
+              for (int i = 0; i < DP; i += 2) {
+                const uint64_t yy = pack2(y[i], y[i + 1]);
+                ss2 = ffma2(yy, yy, ss2);
+              }
+              float ss_lo, ss_hi;
+              unpack2(ss2, ss_lo, ss_hi);
+              const float inv = rsqrtf(fmaxf(ss_lo + ss_hi, 1e-24f));
+              const uint64_t inv2 = pack2(inv, inv);
 #pragma unroll
-              for (int i = 0; i < DP; ++i) y[i] *= inv;
+              for (int i = 0; i < DP; i += 2) unpack2(fmul2(pack2(y[i], y[i + 1]), inv2), y[i], y[i + 1]);
             }
           } else {
             if (p.bias) {
