@@ -179,10 +179,11 @@ class Arm(object):
 
     def step_e2e(self):
         torch = self.torch
+        from openseg3d_b200.ops import predict_labels
         with torch.no_grad():
             d = self.host.cuda(non_blocking=True)
             out = self.model({'points': d, 'batch_size': self.frames})['point_out']
-            self.labels_host.copy_(out.argmax(dim=1).to(torch.uint8), non_blocking=True)   # tools/test.py:56 argmax + .cpu()
+            self.labels_host.copy_(predict_labels(out), non_blocking=True)   # tools/test.py:58 argmax + .cpu()
         torch.cuda.current_stream().synchronize()
 
     def warm(self, n):
@@ -274,7 +275,7 @@ def build_roofline(arm, by, recs, step_ms, pk):
                 'other_kernels_ms_per_step': {k: round(v[0], 3) for k, v in sorted(by.items()) if k not in entries}}
 
     # HBM-bound kernels of stages 1-2 (+ the position-table gather-add): achieved = algorithmic bytes / CUDA-event time
-    hbm_names = ['os3d_voxelize', 'os3d_scatter_max_f32', 'os3d_scatter_mean_f32', 'os3d_gather_rows', 'os3d_subm_table',
+    hbm_names = ['os3d_voxelize', 'os3d_scatter_max_f32', 'os3d_scatter_max_bf16', 'os3d_scatter_max_sorted_bf16', 'os3d_scatter_mean_small_bf16', 'os3d_scatter_mean_f32', 'os3d_gather_rows', 'os3d_subm_table',
                  'os3d_strided_tables', 'os3d_kernel_map_tiles', 'os3d_kernel_map_order', 'os3d_window_partition',
                  'os3d_add_table_rows', 'os3d_gelu_bf16']
     roofline['hbm_kernels'] = {

@@ -64,8 +64,25 @@ int os3d_cart2polar_rows(const float *in, int64_t n, int in_stride, int has_batc
  * output: points per voxel).  counts_in (avg pooling with caller counts) may be NULL. */
 int os3d_scatter_max_f32(const float *feats, const int64_t *ids, int64_t n, int c, float *out, int64_t m, int fix_empty,
                          void *stream);
+/* the same maximum for bf16 features (c % 8 == 0), bf16 voxel features out: feats [n, c] bf16 read as they are (no fp32
+ * copy), ids int32 or int64 (ids_are_i64), acc [m, c] f32 scratch, out [m, c] bf16.  Exact: every maximum is one of the
+ * bf16 inputs.  fix_empty as above (fused into the bf16 write). */
+int os3d_scatter_max_bf16(const void *feats, const void *ids, int ids_are_i64, int64_t n, int c, float *acc, void *out,
+                          int64_t m, int fix_empty, void *stream);
+/* the same result without atomics: point rows sorted by voxel id (cub radix sort, ceil(log2(m + 1)) key bits), each
+ * run of equal ids reduced by one lane group and written once.  keys / keys_sorted [n] uint32, rows / rows_sorted [n]
+ * int32, temp: os3d_scatter_max_sorted_scratch(n, m) bytes.  c % 8 == 0, c <= 2048. */
+int os3d_scatter_max_sorted_scratch(int64_t n, int64_t m, int64_t *temp_bytes);
+int os3d_scatter_max_sorted_bf16(const void *feats, const void *ids, int ids_are_i64, int64_t n, int c, uint32_t *keys,
+                                 uint32_t *keys_sorted, int32_t *rows, int32_t *rows_sorted, void *temp,
+                                 int64_t temp_bytes, void *out, int64_t m, int fix_empty, void *stream);
 int os3d_scatter_mean_f32(const float *feats, const int64_t *ids, int64_t n, int c, float *out, int32_t *counts,
                           const int32_t *counts_in, int64_t m, void *stream);
+/* scatter mean of bf16 rows into a FEW destination rows (m <= 64: the SE layer's per-frame pooling, se_layer.py:17-23):
+ * feats [n, c] bf16 read as they are, c % 8 == 0, ids int32 / int64 (sorted runs make it fast, any order is correct),
+ * out [m, c] f32, counts [m] int32 (output). */
+int os3d_scatter_mean_small_bf16(const void *feats, const void *ids, int ids_are_i64, int64_t n, int c, float *out,
+                                 int32_t *counts, int64_t m, void *stream);
 /* backward of scatter_max, torch_scatter semantics: the gradient of out[v, c] goes to ONE argmax row (the lowest point
  * index among ties); arg: int32 [m * c] scratch.  mean: grad / count. */
 int os3d_scatter_max_bwd_f32(const float *grad_out, const float *feats, const float *out, const int64_t *ids, int64_t n,
@@ -261,11 +278,13 @@ typedef struct {
  *   each grouped position (what the tensor-core attention walks);
  *   level_info: device int32[16] = { n_windows[4], first_window[4], 0,0,0,0, tokens_outside_ranges, n_windows_total,
  *   n_tokens_assigned, tokens_over_capacity }.  (The reference drops over-capacity tokens and then cannot continue
- *   -- SURVEY.md Appendix C; callers treat a non-zero count as an error.) */
+ *   -- SURVEY.md Appendix C; callers treat a non-zero count as an error.)
+ *   pos_idx [m] int32 (may be NULL): row of each voxel in the window's position-embedding table,
+ *   (z * win_y + y) * win_x + x of its in-window coordinates. */
 int os3d_window_partition(const int32_t *idx, int64_t m, int batch, const os3d_window_cfg_t *cfg, int32_t *win_count,
                           int32_t *win_meta, int32_t *block_sums, int64_t n_blocks, int64_t *win_id, int32_t *in_win,
                           int32_t *level, int32_t *win_rank, int32_t *inner, int32_t *order, int32_t *seg_start,
-                          int32_t *seg_len, int32_t *pos_seg, int32_t *level_info, void *stream);
+                          int32_t *seg_len, int32_t *pos_seg, int32_t *level_info, int32_t *pos_idx, void *stream);
 
 /* The same partition over caller-supplied group ids in [0, n_groups) (cfg supplies only the batching levels).
  * replaces: get_inner_win_inds as a stand-alone op (seg3d/ops/ingroup_inds/ingroup_inds.py:7-20): `inner` is the rank. */
@@ -371,6 +390,10 @@ int os3d_knn_query(const float *xyz, const float *new_xyz, int64_t m, int nsampl
  * replaces: WaymoDataset.prepare_voxel_labels (seg3d/datasets/waymo_dataset.py:213-246). */
 int os3d_voxel_majority_labels(const int64_t *pvid, const uint8_t *labels, int64_t n, int64_t m, int ignore, int32_t *hist,
                                int32_t *bad, uint8_t *out, void *stream);
+
+/* Predicted class per point: out[i] = argmax_j x[i, j] as uint8 (ties -> the lowest j).
+ * replaces: torch.argmax(point_out, dim=1) of tools/test.py:58.  x [n, c] bf16 (elem_size 2) or f32 (4), c <= 256. */
+int os3d_argmax_rows(const void *x, int64_t n, int c, int elem_size, uint8_t *out, void *stream);
 
 #ifdef __cplusplus
 }

@@ -37,6 +37,10 @@ SIGNATURES = {
                       PTR, PTR],
     'os3d_cart2polar_rows': [PTR, I64, I32, I32, PTR, PTR],
     'os3d_scatter_max_f32': [PTR, PTR, I64, I32, PTR, I64, I32, PTR],
+    'os3d_scatter_max_bf16': [PTR, PTR, I32, I64, I32, PTR, PTR, I64, I32, PTR],
+    'os3d_scatter_mean_small_bf16': [PTR, PTR, I32, I64, I32, PTR, PTR, I64, PTR],
+    'os3d_scatter_max_sorted_scratch': [I64, I64, ctypes.POINTER(ctypes.c_int64)],
+    'os3d_scatter_max_sorted_bf16': [PTR, PTR, I32, I64, I32, PTR, PTR, PTR, PTR, PTR, I64, PTR, I64, I32, PTR],
     'os3d_scatter_mean_f32': [PTR, PTR, I64, I32, PTR, PTR, PTR, I64, PTR],
     'os3d_scatter_max_bwd_f32': [PTR, PTR, PTR, PTR, I64, I32, I64, PTR, PTR, PTR],
     'os3d_scatter_mean_bwd_f32': [PTR, PTR, PTR, I64, I32, I64, PTR, PTR],
@@ -67,7 +71,7 @@ SIGNATURES = {
     'os3d_wide_linear_plan': [I32, I32, I32, I32, ctypes.POINTER(ctypes.c_int)],
     'os3d_wide_linear_bf16': [PTR, I64, I32, I32, I32, PTR, PTR, PTR, PTR, I64, I32, I32, I32, PTR, I64, PTR],
     'os3d_window_partition': [PTR, I64, I32, ctypes.POINTER(WindowCfg), PTR, PTR, PTR, I64, PTR, PTR, PTR, PTR, PTR, PTR,
-                              PTR, PTR, PTR, PTR, PTR],
+                              PTR, PTR, PTR, PTR, PTR, PTR],
     'os3d_group_partition': [PTR, I64, I64, ctypes.POINTER(WindowCfg), PTR, PTR, PTR, I64, PTR, PTR, PTR, PTR, PTR, PTR, PTR,
                              PTR, PTR],
     'os3d_window_attention_bf16_tc': [PTR, PTR, PTR, I64, I64, I64, I32, I32, PTR, PTR, PTR, PTR, F32, PTR, I64, PTR],
@@ -75,6 +79,7 @@ SIGNATURES = {
     'os3d_window_attention_bf16_v2': [PTR, PTR, PTR, I64, I64, I64, I32, I32, PTR, PTR, PTR, PTR, F32, PTR, I64, PTR],
     'os3d_pos_embed': [PTR, I64, I32, I32, I32, I32, F32, I32, PTR, PTR],
     'os3d_voxel_majority_labels': [PTR, PTR, I64, I64, I32, PTR, PTR, PTR, PTR],
+    'os3d_argmax_rows': [PTR, I64, I32, I32, PTR, PTR],
     'os3d_knn_query': [PTR, PTR, I64, I32, PTR, PTR, I32, PTR, PTR, PTR],
     'os3d_add_table_rows': [PTR, PTR, PTR, I64, I32, I32, PTR, PTR],
     'os3d_gelu_bf16': [PTR, I64, PTR, PTR],
@@ -126,12 +131,12 @@ def stream():
 
 # CUDA kernels launched by each entry point (memsets not counted) -- bench.py's gpu_launches evidence
 KERNELS_PER_CALL = {
-    'os3d_voxelize': 5, 'os3d_cart2polar_rows': 1, 'os3d_scatter_max_f32': 2, 'os3d_scatter_mean_f32': 2,
+    'os3d_voxelize': 5, 'os3d_cart2polar_rows': 1, 'os3d_scatter_max_f32': 2, 'os3d_scatter_max_bf16': 3, 'os3d_scatter_mean_small_bf16': 2, 'os3d_scatter_max_sorted_bf16': 6, 'os3d_scatter_mean_f32': 2,
     'os3d_scatter_max_bwd_f32': 2, 'os3d_scatter_mean_bwd_f32': 1, 'os3d_gather_rows': 1, 'os3d_scatter_add_rows_f32': 1,
     'os3d_hash_build': 1, 'os3d_subm_table': 1, 'os3d_strided_sites': 4, 'os3d_strided_tables': 2,
     'os3d_spconv_fwd_f32': 1, 'os3d_spconv_fwd_bf16': 1, 'os3d_spconv_fwd_bf16_ld': 1, 'os3d_pack_weight_f32': 1, 'os3d_pack_weight_bf16': 1, 'os3d_kernel_map_tiles': 1, 'os3d_kernel_map_order': 2, 'os3d_linear_bf16': 1, 'os3d_linear_tc_bf16': 1, 'os3d_pack_linear_bf16': 1, 'os3d_mlp_chain_bf16': 1, 'os3d_swformer_mlp_bf16': 1,
     'os3d_window_partition': 7, 'os3d_group_partition': 7, 'os3d_pos_embed': 1, 'os3d_qk_normalize': 1,
-    'os3d_window_attention': 1, 'os3d_window_attention_bwd': 2, 'os3d_window_attention_bf16_tc': 1, 'os3d_window_attention_bf16_v2': 1, 'os3d_window_attention_bf16_tc_prenorm': 1, 'os3d_wide_linear_bf16': 1, 'os3d_voxel_majority_labels': 2, 'os3d_layernorm_residual': 1,
+    'os3d_window_attention': 1, 'os3d_window_attention_bwd': 2, 'os3d_window_attention_bf16_tc': 1, 'os3d_window_attention_bf16_v2': 1, 'os3d_window_attention_bf16_tc_prenorm': 1, 'os3d_wide_linear_bf16': 1, 'os3d_voxel_majority_labels': 2, 'os3d_argmax_rows': 1, 'os3d_layernorm_residual': 1,
 }
 _launches = 0
 PROFILE = None      # bench.py sets this to a list to collect (name, start_event, end_event, work) per call

@@ -38,7 +38,7 @@ def voxelize_batch(points, voxel_size, point_cloud_range, has_batch=True):
     block_sums = torch.empty(nb.value + 1, dtype=torch.int32, device=dev)
     coors = torch.empty((max(n, 1), 4), dtype=torch.int32, device=dev)
     pvid = torch.empty(n, dtype=torch.int64, device=dev)
-    num = torch.zeros(1, dtype=torch.int32, device=dev)
+    num = torch.empty(1, dtype=torch.int32, device=dev)                # written by the entry point
     _lib.call('os3d_voxelize', points, n, stride, int(has_batch), float(pcr[0]), float(pcr[1]), float(pcr[2]),
               float(vs[0]), float(vs[1]), float(vs[2]), int(grid[0]), int(grid[1]), int(grid[2]), table, cap.value,
               slot_of, block_sums, nb.value, coors, pvid, num,

@@ -40,6 +40,44 @@ __global__ void label_argmax_kernel(const int32_t *__restrict__ hist, int64_t m,
   out[v] = best_bin < 0 ? (uint8_t)ignore : (best_bin == kLabelBins - 1 ? (uint8_t)ignore : (uint8_t)best_bin);
 }
 
+// Predicted label per point: argmax over the class logits of each row (tools/test.py:58, torch.argmax(point_out, dim=1)),
+// written as uint8.  Ties -> the lowest class index; NaN never wins (a row of NaNs gives 0).  The rows of a block are one
+// contiguous, 16-byte aligned span of memory (256 rows x c elements): it is staged in shared memory with 16-byte loads
+// and each thread then scans its own row there -- the 46-byte rows of the 23-class head would otherwise be read as 23
+// scattered 2-byte loads per thread.
+constexpr int kArgRows = 256;
+template <typename T>
+__device__ __forceinline__ float logit_to_float(T v);
+template <>
+__device__ __forceinline__ float logit_to_float<float>(float v) { return v; }
+template <>
+__device__ __forceinline__ float logit_to_float<__nv_bfloat16>(__nv_bfloat16 v) { return __bfloat162float(v); }
+
+template <typename T>
+__global__ void __launch_bounds__(kArgRows) argmax_rows_kernel(const T *__restrict__ x, int64_t n, int c, int rows_per_block,
+                                                               uint8_t *__restrict__ out) {
+  extern __shared__ uint4 stage4[];
+  T *stage = reinterpret_cast<T *>(stage4);
+  const int64_t row0 = (int64_t)blockIdx.x * rows_per_block;
+  const int rows = (int)min((int64_t)rows_per_block, n - row0);
+  const int64_t elems = (int64_t)rows * c;
+  const T *src = x + row0 * c;                                  // 16-byte aligned: rows_per_block is a multiple of 8
+  constexpr int kPer16 = 16 / (int)sizeof(T);
+  const int n16 = (int)(elems / kPer16);
+  for (int i = threadIdx.x; i < n16; i += kArgRows) stage4[i] = __ldg(reinterpret_cast<const uint4 *>(src) + i);
+  for (int i = n16 * kPer16 + threadIdx.x; i < elems; i += kArgRows) stage[i] = src[i];
+  __syncthreads();
+  if ((int)threadIdx.x >= rows) return;
+  const T *r = stage + (int)threadIdx.x * c;
+  float best = -INFINITY;
+  int arg = 0;
+  for (int j = 0; j < c; ++j) {
+    const float v = logit_to_float<T>(r[j]);
+    if (v > best) { best = v; arg = j; }
+  }
+  out[row0 + threadIdx.x] = (uint8_t)arg;
+}
+
 }  // namespace os3d
 
 using namespace os3d;
@@ -53,6 +91,20 @@ extern "C" int os3d_voxel_majority_labels(const int64_t *pvid, const uint8_t *la
   OS3D_CUDA(cudaMemsetAsync(bad, 0, sizeof(int32_t), st));
   if (n > 0) label_hist_kernel<<<(unsigned)cdiv(n, 256), 256, 0, st>>>(pvid, labels, n, m, ignore, hist, bad);
   label_argmax_kernel<<<(unsigned)cdiv(m, 256), 256, 0, st>>>(hist, m, ignore, out);
+  OS3D_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int os3d_argmax_rows(const void *x, int64_t n, int c, int elem_size, uint8_t *out, void *stream) {
+  if (n < 0 || c < 1 || c > 256 || (elem_size != 2 && elem_size != 4)) return OS3D_ERR_BAD_ARG;
+  if (n == 0) return 0;
+  cudaStream_t st = (cudaStream_t)stream;
+  int rows = kArgRows;                                               // rows per block: a multiple of 8 within 48 KB
+  while ((size_t)rows * c * elem_size > 48 * 1024) rows -= 8;
+  const size_t smem = (size_t)rows * c * elem_size;
+  const unsigned grid = (unsigned)cdiv(n, rows);
+  if (elem_size == 2) argmax_rows_kernel<__nv_bfloat16><<<grid, kArgRows, smem, st>>>((const __nv_bfloat16 *)x, n, c, rows, out);
+  else argmax_rows_kernel<float><<<grid, kArgRows, smem, st>>>((const float *)x, n, c, rows, out);
   OS3D_LAUNCH_CHECK();
   return 0;
 }

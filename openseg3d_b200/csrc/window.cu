@@ -28,7 +28,7 @@ __device__ __forceinline__ int level_of(const os3d_window_cfg_t &cfg, int cnt) {
 
 __global__ void win_assign_kernel(const int4 *__restrict__ idx, int64_t m, os3d_window_cfg_t cfg,
                                   int64_t *__restrict__ win_id, int32_t *__restrict__ in_win,
-                                  int32_t *__restrict__ win_count) {
+                                  int32_t *__restrict__ win_count, int32_t *__restrict__ pos_idx) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= m) return;
   const int4 c = __ldg(idx + i);  // (b, z, y, x)
@@ -40,6 +40,8 @@ __global__ void win_assign_kernel(const int4 *__restrict__ idx, int64_t m, os3d_
   in_win[i * 3 + 0] = sz - wz * cfg.win_z;
   in_win[i * 3 + 1] = sy - wy * cfg.win_y;
   in_win[i * 3 + 2] = sx - wx * cfg.win_x;
+  // row of the window's position-embedding table: (z * win_y + y) * win_x + x
+  if (pos_idx) pos_idx[i] = ((sz - wz * cfg.win_z) * cfg.win_y + (sy - wy * cfg.win_y)) * cfg.win_x + (sx - wx * cfg.win_x);
   atomicAdd(win_count + w, 1);
 }
 
@@ -313,7 +315,7 @@ extern "C" int os3d_window_partition(const int32_t *idx, int64_t m, int batch, c
                                      int32_t *win_count, int32_t *win_meta, int32_t *block_sums, int64_t n_blocks,
                                      int64_t *win_id, int32_t *in_win, int32_t *level, int32_t *win_rank,
                                      int32_t *inner, int32_t *order, int32_t *seg_start, int32_t *seg_len,
-                                     int32_t *pos_seg, int32_t *level_info, void *stream) {
+                                     int32_t *pos_seg, int32_t *level_info, int32_t *pos_idx, void *stream) {
   cudaStream_t st = (cudaStream_t)stream;
   const os3d_window_cfg_t cfg = *cfg_p;
   const int64_t n_win = (int64_t)batch * cfg.nwin_x * cfg.nwin_y * cfg.nwin_z;
@@ -321,7 +323,7 @@ extern "C" int os3d_window_partition(const int32_t *idx, int64_t m, int batch, c
   OS3D_CUDA(cudaMemsetAsync(win_count, 0, sizeof(int32_t) * (size_t)n_win, st));
   OS3D_CUDA(cudaMemsetAsync(level_info, 0, sizeof(int32_t) * 16, st));
   if (m == 0) return 0;
-  win_assign_kernel<<<(unsigned)cdiv(m, 256), 256, 0, st>>>((const int4 *)idx, m, cfg, win_id, in_win, win_count);
+  win_assign_kernel<<<(unsigned)cdiv(m, 256), 256, 0, st>>>((const int4 *)idx, m, cfg, win_id, in_win, win_count, pos_idx);
   return partition_common(win_id, m, n_win, cfg, win_count, win_meta, block_sums, n_blocks, level, win_rank, inner, order,
                           seg_start, seg_len, pos_seg, level_info, st);
 }

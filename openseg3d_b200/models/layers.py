@@ -214,9 +214,11 @@ class PosDict(dict):
     @property
     def pos_idx(self):
         if self._idx is None:
-            wx, wy, wz = [int(w) for w in self._layer.window_shape]
-            iw = self._seg.in_win                      # (z, y, x)
-            self._idx = ((iw[:, 0] * wy + iw[:, 1]) * wx + iw[:, 2]).contiguous()
+            self._idx = getattr(self._seg, 'pos_idx', None)          # written by os3d_window_partition
+            if self._idx is None:
+                wx, wy, wz = [int(w) for w in self._layer.window_shape]
+                iw = self._seg.in_win                      # (z, y, x)
+                self._idx = ((iw[:, 0] * wy + iw[:, 1]) * wx + iw[:, 2]).contiguous()
         return self._idx
 
 
@@ -304,6 +306,7 @@ class SparseWindowPartitionLayer(nn.Module):
         seg = WindowSegments(cfg, self.batching_info, m)
         seg.win_id = torch.empty(m, dtype=torch.int64, device=dev)
         seg.in_win = torch.empty((m, 3), **i32)
+        seg.pos_idx = torch.empty(m, **i32)              # row in the window's position-embedding table
         seg.level, seg.win_rank, seg.inner = torch.empty(m, **i32), torch.empty(m, **i32), torch.empty(m, **i32)
         seg.order = torch.empty(m, **i32)
         seg.seg_start, seg.seg_len = torch.empty(m + 1, **i32), torch.empty(m + 1, **i32)
@@ -313,8 +316,8 @@ class SparseWindowPartitionLayer(nn.Module):
         block_sums = torch.empty((nb + 1) * 5, **i32)
         _lib.call('os3d_window_partition', indices, m, batch_size, ctypes.byref(cfg), win_count, win_meta, block_sums, nb,
                   seg.win_id, seg.in_win, seg.level, seg.win_rank, seg.inner, seg.order, seg.seg_start, seg.seg_len,
-                  seg.pos_seg, seg.level_info,
-                  work=lambda: m * (16 + 4 * 12) + 8 * n_win)       # coords in; ids / ranks / order / segments out; histogram
+                  seg.pos_seg, seg.level_info, seg.pos_idx,
+                  work=lambda: m * (16 + 4 * 13) + 8 * n_win)       # coords in; ids / ranks / order / segments out; histogram
         return seg
 
     @torch.no_grad()

@@ -49,3 +49,16 @@ def aux_voxel_labels(voxel_labels, voxel_coords, aux_voxel_coords, batch_size, v
     aux_offset = (aux_voxel_coords[:, 0].long()[None, :] <= b[:, None]).sum(dim=1).int()
     idx, _ = knn_query(1, centers, aux_centers, offset, aux_offset)
     return voxel_labels[idx.reshape(-1).long()]
+
+
+def predict_labels(point_out):
+    """tools/test.py:58 -- ``torch.argmax(point_out, dim=1)`` as uint8 labels [N] (ties -> the lowest class), one pass over
+    the logits (os3d_argmax_rows) instead of torch's generic reduce + an int64 -> uint8 cast."""
+    _lib.require_cuda(point_out)
+    if point_out.dim() != 2 or point_out.dtype not in (torch.bfloat16, torch.float32):
+        raise RuntimeError('predict_labels takes [N, classes] bf16 / fp32 logits')
+    x = point_out.contiguous()
+    n, c = x.shape
+    out = torch.empty(n, dtype=torch.uint8, device=x.device)
+    _lib.call('os3d_argmax_rows', x, n, c, x.element_size(), out, work=lambda: n * c * x.element_size() + n)
+    return out

@@ -62,7 +62,7 @@ def build_subm_rulebook(x):
     m = x.indices.shape[0]
     table, cap = _table_of(x)
     nbr = torch.empty((m, 27), dtype=torch.int32, device=x.indices.device)
-    pairs = torch.zeros(1, dtype=torch.int32, device=x.indices.device)
+    pairs = torch.empty(1, dtype=torch.int32, device=x.indices.device)     # zeroed by the entry point
     z, y, xx = x.spatial_shape
     _lib.call('os3d_subm_table', x.indices, m, z, y, xx, table, cap, nbr, pairs, work=lambda: m * (16 + 27 * 4))
     return SubmRulebook(nbr, pairs, x.indices, list(x.spatial_shape))
@@ -83,7 +83,7 @@ def build_strided_rulebook(x):
     block_sums = torch.empty(n_blocks + 1, dtype=torch.int32, device=dev)
     cap_out = min(8 * m, cells) + 1
     out_idx = torch.empty((cap_out, 4), dtype=torch.int32, device=dev)
-    num = torch.zeros(1, dtype=torch.int32, device=dev)
+    num = torch.empty(1, dtype=torch.int32, device=dev)                # written by the entry point
     _lib.call('os3d_strided_sites', x.indices, m, x.batch_size, oz, oy, ox, bitmap, n_words, prefix, block_sums, n_blocks,
               out_idx, cap_out, num)
     table, cap = _table_of(x)
@@ -91,7 +91,7 @@ def build_strided_rulebook(x):
     out_idx = out_idx[:m_out]
     fwd = torch.empty((m_out, 27), dtype=torch.int32, device=dev)
     inv = torch.empty((m, 27), dtype=torch.int32, device=dev)
-    pairs = torch.zeros(1, dtype=torch.int32, device=dev)
+    pairs = torch.empty(1, dtype=torch.int32, device=dev)              # zeroed by the entry point
     _lib.call('os3d_strided_tables', x.indices, m, sz, sy, sx, table, cap, out_idx, m_out, oz, oy, ox, bitmap, prefix, fwd,
               inv, pairs, work=lambda: (m + m_out) * (16 + 27 * 4))
     return StridedRulebook(x.indices, [sz, sy, sx], out_idx, [oz, oy, ox], fwd, inv, pairs)

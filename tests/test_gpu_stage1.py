@@ -103,6 +103,51 @@ def test_scatter_max_bit_exact_and_mean(c):
     assert torch.equal(mx2, oracle.scatter_reduce(feats, ids2, 'max')) and bool((mx2[5] == 0).all())
 
 
+@pytest.mark.parametrize('impl', ['sorted', 'atomic'])
+@pytest.mark.parametrize('c,idt', [(64, torch.int32), (64, torch.int64), (8, torch.int32), (128, torch.int64)])
+def test_scatter_max_bf16_inputs_exact(c, idt, impl, monkeypatch):
+    """bf16 inference path of VFE (vfe.py:24-25): bf16 point features reduced as they are, bf16 voxel features out --
+    exactly the maximum of the inputs, empty rows 0 (or -inf without fix_empty), ids -1 skipped."""
+    from openseg3d_b200.ops import scatter_max, pooling
+    from oracle import oracle
+    monkeypatch.setattr(pooling, '_MAX_IMPL', impl)
+    torch.manual_seed(c)
+    n, m = 60000, 9000
+    feats = torch.randn(n, c).bfloat16()
+    ids = torch.randint(-1, m, (n,))
+    ids[ids == 7] = -1                              # voxel 7 stays empty
+    ids[0] = m - 1                                  # the oracle sizes its output by the largest id
+    ref = oracle.scatter_reduce(feats.float(), ids, 'max')
+    got = scatter_max(feats.cuda(), ids.to(idt).cuda(), m)
+    assert got.dtype == torch.bfloat16
+    assert torch.equal(got.float().cpu(), ref) and bool((got[7] == 0).all())
+    raw = scatter_max(feats.cuda(), ids.to(idt).cuda(), m, fix_empty=False)
+    seen = torch.zeros(m, dtype=torch.bool).index_fill_(0, ids[ids >= 0], True)
+    assert not bool(seen[7]) and bool(torch.isneginf(raw[~seen.cuda()].float()).all())
+    assert torch.equal(raw.float().cpu()[seen], ref[seen])
+    assert scatter_max(feats[:0].cuda(), ids[:0].to(idt).cuda(), 5).abs().sum().item() == 0
+
+
+@pytest.mark.parametrize('c,idt,m', [(64, torch.int64, 8), (128, torch.int32, 3), (8, torch.int64, 64)])
+def test_scatter_mean_bf16_rows_into_few(c, idt, m):
+    """SE layer pooling in bf16 inference (se_layer.py:17-23): per-frame mean of bf16 point features, fp32 out."""
+    from openseg3d_b200.ops import scatter_mean
+    from oracle import oracle
+    torch.manual_seed(c + m)
+    n = 70000
+    feats = torch.randn(n, c).bfloat16()
+    ids = torch.sort(torch.randint(0, m, (n,))).values            # frames arrive in order
+    ids[::97] = -1
+    ids[-1] = m - 1
+    ref = oracle.scatter_reduce(feats.float(), ids, 'mean')
+    got = scatter_mean(feats.cuda(), ids.to(idt).cuda(), m)
+    assert got.dtype == torch.float32
+    torch.testing.assert_close(got.cpu(), ref, rtol=1e-4, atol=1e-6)
+    shuffled = torch.randperm(n)                                  # any order is correct, sorted runs are just faster
+    got2 = scatter_mean(feats[shuffled].cuda(), ids[shuffled].to(idt).cuda(), m)
+    torch.testing.assert_close(got2.cpu(), ref, rtol=1e-4, atol=1e-6)
+
+
 def test_vfe_and_pooling_api():
     from openseg3d_b200.models import VFE
     from openseg3d_b200.ops import voxel_avg_pooling, voxel_max_pooling
@@ -159,7 +204,7 @@ def test_scatter_max_backward_with_ties_routes_to_one_row():
     torch.manual_seed(2)
     n, m, c = 4000, 300, 8
     feats = torch.randn(n, c).bfloat16().float()                       # 8-bit mantissa: many collisions
-    feats[::3] = feats[1::3][:feats[::3].shape[0]]                     # and exact duplicates
+    feats[0:3999:3] = feats[1:4000:3]                                  # and exact duplicates (1333 rows each)
     ids = torch.randint(0, m, (n,))
     a = feats.clone().cuda().requires_grad_(True)
     out = scatter_max(a, ids.cuda(), m)

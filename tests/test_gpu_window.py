@@ -40,6 +40,10 @@ def test_partition_bit_exact_vs_reference(g):
         inds = info[f'flat2win_inds_shift{s}'].materialize()
         seg = inds['segments']
         li = seg.check_no_drop()
+        # row of each voxel in the window's position table, as the reference indexes its embedding: (z * wy + y) * wx + x
+        iw = g[f'inwin_s{s}'].astype(np.int64)
+        wx, wy, wz = [int(w) for w in layer.window_shape]
+        assert np.array_equal(seg.pos_idx.cpu().numpy(), (iw[:, 0] * wy + iw[:, 1]) * wx + iw[:, 2])
         levels = [bl for bl in binfo if f'slot_s{s}_l{bl}' in g]
         assert sorted(inds.levels()) == sorted(levels)
         for bl in levels:

@@ -71,3 +71,25 @@ def test_gpu_aux_voxel_labels_match_oracle(g):
     ref = oracle.aux_voxel_labels(labels, c1, c8, 2, vs, pcr)
     out = aux_voxel_labels(torch.from_numpy(labels).cuda(), torch.from_numpy(c1).cuda(), torch.from_numpy(c8).cuda(), 2, vs, pcr)
     assert np.array_equal(out.cpu().numpy(), ref)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize('dtype', ['bf16', 'f32'])
+@pytest.mark.parametrize('n,c', [(0, 23), (1, 23), (255, 23), (256, 23), (100003, 23), (5000, 22), (777, 7), (4097, 64)])
+def test_predict_labels_matches_first_argmax(n, c, dtype):
+    """tools/test.py:58: argmax over the class logits of each point; ties resolve to the lowest class index."""
+    import torch
+    from openseg3d_b200.ops import predict_labels
+    torch.manual_seed(n + c)
+    x = torch.randn(n, c)
+    if dtype == 'bf16':
+        x = x.bfloat16()                    # 8-bit mantissa: ties are common
+    if n > 3:
+        x[1] = x[1, 0]                      # a whole row of ties -> class 0
+        x[2, c - 1] = x[2].max()            # a tie between an inner class and the last one -> the inner one
+    xf = x.float()
+    is_max = xf == xf.max(dim=1, keepdim=True).values
+    expect = torch.where(is_max, torch.arange(c)[None].expand(n, c), c).min(dim=1).values.to(torch.uint8) if n else torch.empty(0, dtype=torch.uint8)
+    got = predict_labels(x.cuda())
+    assert got.dtype == torch.uint8 and got.shape == (n,)
+    assert torch.equal(got.cpu(), expect)
