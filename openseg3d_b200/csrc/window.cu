@@ -83,6 +83,7 @@ __global__ void __launch_bounds__(kScanThreads) win_apply_kernel(int32_t *__rest
                                                                   const int32_t *__restrict__ block_sums,
                                                                   int64_t n_blocks, int32_t *__restrict__ win_meta,
                                                                   int32_t *__restrict__ seg_start,
+                                                                  int32_t *__restrict__ seg_len,
                                                                   int32_t *__restrict__ level_info, int64_t m) {
   const int64_t base = (int64_t)blockIdx.x * kScanTile + threadIdx.x * kScanItems;
   int cnt[kScanItems], v[kScanItems][kLanes], s[kLanes] = {0, 0, 0, 0, 0}, ex[kLanes];
@@ -116,6 +117,7 @@ __global__ void __launch_bounds__(kScanThreads) win_apply_kernel(int32_t *__rest
       win_meta[w * 3 + 1] = lvl;
       win_meta[w * 3 + 2] = slot;
       seg_start[slot] = ex[0];
+      seg_len[slot] = cnt[t];
     } else {
       win_meta[w * 3 + 0] = -1;  // empty, or occupancy outside every batching range (tokens dropped)
       win_meta[w * 3 + 1] = -1;
@@ -150,35 +152,39 @@ __global__ void win_fill_kernel(const int64_t *__restrict__ win_id, int64_t m, c
   order[off + atomicAdd(cursor + w, 1)] = (int32_t)i;
 }
 
-// One warp per non-empty window: sort the segment ascending by voxel row (rank counting in shared memory), write
-// the per-voxel level / window rank / in-window rank, the window's length and the number of over-capacity tokens.
+// One warp per NON-EMPTY window (segment slot), warps striding over the level-major segment table: sort the segment
+// ascending by voxel row (rank counting in shared memory), write the per-voxel level / window rank / in-window rank and the
+// number of over-capacity tokens.  (The first version launched one warp per grid CELL -- 1.3 M windows at level 1 of an
+// 8-frame batch, 17 k of them occupied: 0.22 ms of empty warps per call.)
 constexpr int kSortWarps = 8;
 constexpr int kMaxSeg = 1024;  // >= any max_tokens the reference uses (800)
 
-__global__ void __launch_bounds__(kSortWarps * 32) win_sort_kernel(const int64_t *__restrict__ win_id,
-                                                                   const int32_t *__restrict__ win_meta,
-                                                                   const int32_t *__restrict__ cursor_counts,
+__global__ void __launch_bounds__(kSortWarps * 32) win_sort_kernel(const int32_t *__restrict__ seg_start,
+                                                                   const int32_t *__restrict__ seg_len,
                                                                    os3d_window_cfg_t cfg, int32_t *__restrict__ order,
-                                                                   int32_t *__restrict__ seg_len,
                                                                    int32_t *__restrict__ level,
                                                                    int32_t *__restrict__ win_rank,
                                                                    int32_t *__restrict__ inner,
                                                                    int2 *__restrict__ pos_seg,
-                                                                   int32_t *__restrict__ level_info, int64_t n_win) {
+                                                                   int32_t *__restrict__ level_info) {
   __shared__ int32_t buf[kSortWarps][kMaxSeg];
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-  const int64_t w = (int64_t)blockIdx.x * kSortWarps + wid;
-  if (w >= n_win) return;
-  const int32_t off = __ldg(win_meta + w * 3);
-  if (off < 0) return;
-  const int lvl = __ldg(win_meta + w * 3 + 1), slot = __ldg(win_meta + w * 3 + 2);
-  const int n = __ldg(cursor_counts + w);  // the fill cursor ended at the window's occupancy
-  const int first_of_level = level_info[4 + lvl];
-  if (lane == 0) seg_len[slot] = n;
+  const int n_slots = level_info[13];
+  int first[4], has[4];
+#pragma unroll
+  for (int l = 0; l < 4; ++l) { first[l] = level_info[4 + l]; has[l] = level_info[l] > 0; }
+  int dropped = 0;
+  for (int slot = blockIdx.x * kSortWarps + wid; slot < n_slots; slot += gridDim.x * kSortWarps) {
+  int lvl = 0;
+#pragma unroll
+  for (int l = 1; l < 4; ++l) if (has[l] && slot >= first[l]) lvl = l;
+  const int first_of_level = first[lvl];
+  const int32_t off = __ldg(seg_start + slot);
+  const int n = __ldg(seg_len + slot);
   int32_t *seg = order + off;
   for (int t = lane; t < n; t += 32) pos_seg[off + t] = make_int2(off, n);  // (window start, length) per position
+  __syncwarp();
   const int cap = cfg.lvl_tokens[lvl];
-  int dropped = 0;
   if (n <= 64) {
     for (int t = lane; t < n; t += 32) buf[wid][t] = seg[t];
     __syncwarp();
@@ -230,9 +236,10 @@ __global__ void __launch_bounds__(kSortWarps * 32) win_sort_kernel(const int64_t
       dropped += r >= cap;
     }
   }
+  __syncwarp();               // the staging buffer is reused by the next segment of this warp
+  }
   dropped = __reduce_add_sync(0xffffffffu, dropped);
   if (lane == 0 && dropped) atomicAdd(level_info + 15, dropped);
-  (void)win_id;
 }
 
 __global__ void mark_unassigned_kernel(const int64_t *__restrict__ win_id, int64_t m, const int32_t *__restrict__ win_meta,
@@ -301,12 +308,13 @@ static int partition_common(const int64_t *win_id, int64_t m, int64_t n_win, con
   win_count_kernel<<<(unsigned)n_blocks, kScanThreads, 0, st>>>(win_count, n_win, cfg, block_sums);
   scan_block_sums_multi_kernel<<<1, kScanThreads, 0, st>>>(block_sums, n_blocks, kLanes);
   win_apply_kernel<<<(unsigned)n_blocks, kScanThreads, 0, st>>>(win_count, n_win, cfg, block_sums, n_blocks, win_meta,
-                                                                seg_start, level_info, m);
+                                                                seg_start, seg_len, level_info, m);
   win_fill_kernel<<<gv, 256, 0, st>>>(win_id, m, win_meta, win_count, order);
   mark_unassigned_kernel<<<gv, 256, 0, st>>>(win_id, m, win_meta, level, win_rank, inner);
-  win_sort_kernel<<<(unsigned)cdiv(n_win, kSortWarps), kSortWarps * 32, 0, st>>>(win_id, win_meta, win_count, cfg, order,
-                                                                                  seg_len, level, win_rank, inner,
-                                                                                  (int2 *)pos_seg, level_info, n_win);
+  // at most one segment per voxel; 148 SMs x 8 blocks of 8 warps stride over the occupied ones
+  const unsigned sort_blocks = (unsigned)std::min<int64_t>(cdiv(std::min<int64_t>(n_win, m), kSortWarps), 148 * 8);
+  win_sort_kernel<<<sort_blocks, kSortWarps * 32, 0, st>>>(seg_start, seg_len, cfg, order, level, win_rank, inner,
+                                                           (int2 *)pos_seg, level_info);
   OS3D_LAUNCH_CHECK();
   return 0;
 }
