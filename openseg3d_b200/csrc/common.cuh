@@ -49,6 +49,59 @@ __device__ __forceinline__ float gelu_erf_fast(float x) {
   return x * (x >= 0.0f ? 1.0f - half_erfc : half_erfc);             // x * Phi(x)
 }
 
+// Two GELUs at once on the two-wide FP32 instructions of sm_100 (fma / mul / add .f32x2): the same erf approximation,
+// 9 instructions per element instead of 14 (the MLP epilogues are bound by their instruction count).  The result is put
+// together as x Phi(x) = x / 2 + |x| (1/2 - Phi(-|x|)), which needs no select; its absolute error against x * Phi(x) is
+// below |x| 2^-25 (for x < -5, where x Phi(x) itself is below 2e-6).  y = gelu(a + b) for both lanes.
+__device__ __forceinline__ void gelu_erf_fast2(float a0, float a1, float b0, float b1, float &y0, float &y1) {
+  uint64_t x2, u2, t2, e2, p2;
+  asm("{\n\t"
+      ".reg .b64 a, b;\n\t"
+      "mov.b64 a, {%1, %2};\n\t"
+      "mov.b64 b, {%3, %4};\n\t"
+      "add.rn.f32x2 %0, a, b;\n\t"
+      "}" : "=l"(x2) : "f"(a0), "f"(a1), "f"(b0), "f"(b1));
+  asm("and.b64 %0, %1, 0x7fffffff7fffffff;" : "=l"(u2) : "l"(x2));                          // |x|
+  float d0, d1, u0, u1, t0, t1, e0, e1;
+  {
+    uint64_t den2, sq2;
+    const uint64_t kp = 0x3e6d33883e6d3388ull;      // {0.23164189f, 0.23164189f}
+    const uint64_t k1 = 0x3f8000003f800000ull;      // {1, 1}
+    const uint64_t ke = 0xbf38aa3bbf38aa3bull;      // {-0.7213475f, -0.7213475f} = -log2(e) / 2
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(den2) : "l"(u2), "l"(kp), "l"(k1));
+    asm("mul.rn.f32x2 %0, %1, %1;" : "=l"(sq2) : "l"(u2));
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(sq2) : "l"(sq2), "l"(ke));
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(d0), "=f"(d1) : "l"(den2));
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(u0), "=f"(u1) : "l"(sq2));
+  }
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t0) : "f"(d0));
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t1) : "f"(d1));
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e0) : "f"(u0));
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e1) : "f"(u1));
+  asm("mov.b64 %0, {%1, %2};" : "=l"(t2) : "f"(t0), "f"(t1));
+  asm("mov.b64 %0, {%1, %2};" : "=l"(e2) : "f"(e0), "f"(e1));
+  {
+    const uint64_t c5 = 0x3f07dc223f07dc22ull;      // 0.5307027145
+    const uint64_t c4 = 0xbf3a00e3bf3a00e3ull;      // -0.7265760135
+    const uint64_t c3 = 0x3f35f0e33f35f0e3ull;      // 0.7107068705
+    const uint64_t c2 = 0xbe11a98ebe11a98eull;      // -0.142248368
+    const uint64_t c1 = 0x3e0279063e027906ull;      // 0.127414796
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(p2) : "l"(c5), "l"(t2), "l"(c4));
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(p2) : "l"(p2), "l"(t2), "l"(c3));
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(p2) : "l"(p2), "l"(t2), "l"(c2));
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(p2) : "l"(p2), "l"(t2), "l"(c1));
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(p2) : "l"(p2), "l"(t2));
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(p2) : "l"(p2), "l"(e2));                           // Phi(-|x|)
+    const uint64_t kh = 0x3f0000003f000000ull;      // {0.5, 0.5}
+    const uint64_t kn = 0xbf800000bf800000ull;      // {-1, -1}
+    uint64_t w2, hx2, y2;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(w2) : "l"(p2), "l"(kn), "l"(kh));               // 1/2 - Phi(-|x|)
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(hx2) : "l"(x2), "l"(kh));                          // x / 2
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(y2) : "l"(u2), "l"(w2), "l"(hx2));
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(y0), "=f"(y1) : "l"(y2));
+  }
+}
+
 // Exclusive scan of one int per thread across a 256-thread block. Returns exclusive prefix; total in *total.
 __device__ __forceinline__ int block_excl_scan_256(int v, int *total) {
   __shared__ int warp_sums[8];

@@ -419,8 +419,9 @@ __global__ void __launch_bounds__(kThreads, 1) swformer_mlp_tc_kernel(const __gr
           const float y0 = __uint_as_float(v[4 * q4 + 0]) + b.x, y1 = __uint_as_float(v[4 * q4 + 1]) + b.y;
           const float y2 = __uint_as_float(v[4 * q4 + 2]) + b.z, y3 = __uint_as_float(v[4 * q4 + 3]) + b.w;
 #else
-          const float y0 = gelu_erf_fast(__uint_as_float(v[4 * q4 + 0]) + b.x), y1 = gelu_erf_fast(__uint_as_float(v[4 * q4 + 1]) + b.y);
-          const float y2 = gelu_erf_fast(__uint_as_float(v[4 * q4 + 2]) + b.z), y3 = gelu_erf_fast(__uint_as_float(v[4 * q4 + 3]) + b.w);
+          float y0, y1, y2, y3;
+          gelu_erf_fast2(__uint_as_float(v[4 * q4 + 0]), __uint_as_float(v[4 * q4 + 1]), b.x, b.y, y0, y1);
+          gelu_erf_fast2(__uint_as_float(v[4 * q4 + 2]), __uint_as_float(v[4 * q4 + 3]), b.z, b.w, y2, y3);
 #endif
           const __nv_bfloat162 h0 = __floats2bfloat162_rn(y0, y1), h1 = __floats2bfloat162_rn(y2, y3);
           o[2 * q4] = *reinterpret_cast<const uint32_t *>(&h0);

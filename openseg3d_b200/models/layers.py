@@ -27,6 +27,7 @@ _MLP_MODE = os.environ.get('OS3D_MLP_CHAIN', '1')
 _QKV_MODE = os.environ.get('OS3D_QKV', '1')             # '0': in-projections as library GEMMs + separate table add (A-B runs)
 # 'v1' (default): attention_tc.cu, one CTA per (128-query tile, head), 4-8 CTAs per SM.  'v2': attention_v2.cu, the
 # warp-specialised all-heads-per-CTA design -- parity-tested, but measured slower at levels 1-2
+_TRAIN_TC = os.environ.get('OS3D_TRAIN_ATTN_TC', '1') != '0'      # training forward on the tensor-core kernel (bf16, no dropout)
 _ATTN_IMPL = os.environ.get('OS3D_ATTN', 'v1')
 
 
@@ -362,11 +363,30 @@ class _WindowAttentionFunction(torch.autograd.Function):
     def forward(ctx, qn, kn, v, tau, tau_min, heads, seg, drop_p, seed):
         m, c = qn.shape
         qn, kn, v = qn.contiguous(), kn.contiguous(), v.contiguous()
-        out = torch.empty_like(qn)
         tau32 = tau.detach().float().reshape(1).contiguous()
-        _lib.call('os3d_window_attention', qn, kn, v, c, c, m, c, heads, seg.order, seg.seg_start, seg.seg_len,
-                  seg.level_info, ctypes.byref(seg.lvl_tokens), tau32, float(tau_min), float(drop_p), int(seed),
-                  qn.element_size(), out)
+        d = c // heads
+        dp = (d + 15) // 16 * 16
+        if qn.dtype == torch.bfloat16 and drop_p == 0 and dp <= 48 and m > 0 and _TRAIN_TC:
+            # forward on the tensor cores (os3d_window_attention_bf16_tc_prenorm): heads zero-padded to the MMA's K granule
+            # in one buffer (the padding changes neither dot products nor norms), the padded output cut back to [M, C].
+            # The backward kernel recomputes the probabilities from q / k / v and this output.
+            if dp == d:
+                qkv = torch.cat([qn, kn, v], dim=1)
+            else:
+                qkv = torch.zeros((m, 3 * heads, dp), dtype=qn.dtype, device=qn.device)
+                qkv[:, :, :d] = torch.cat([qn, kn, v], dim=1).view(m, 3 * heads, d)
+                qkv = qkv.view(m, 3 * heads * dp)
+            hd = heads * dp
+            out_p = torch.empty((m, hd), dtype=qn.dtype, device=qn.device)
+            _lib.call('os3d_window_attention_bf16_tc_prenorm', qkv, _lib._Raw(qkv.data_ptr() + hd * 2),
+                      _lib._Raw(qkv.data_ptr() + 2 * hd * 2), 3 * hd, 3 * hd, m, heads, dp, seg.order, seg.pos_seg,
+                      seg.level_info, tau32, float(tau_min), out_p, hd)
+            out = out_p if dp == d else out_p.view(m, heads, dp)[:, :, :d].reshape(m, c)
+        else:
+            out = torch.empty_like(qn)
+            _lib.call('os3d_window_attention', qn, kn, v, c, c, m, c, heads, seg.order, seg.seg_start, seg.seg_len,
+                      seg.level_info, ctypes.byref(seg.lvl_tokens), tau32, float(tau_min), float(drop_p), int(seed),
+                      qn.element_size(), out)
         ctx.save_for_backward(qn, kn, v, out, tau32)
         ctx.args = (tau_min, heads, seg, drop_p, seed, tau.shape, tau.dtype)
         return out
