@@ -280,7 +280,15 @@ __global__ void __launch_bounds__(kThreads, 2) spconv_tc_kernel(const Params p) 
   }
   if (warp < kEpiWarps) {
     // ================================ epilogue ================================
-    mbar_wait(accum_bar, 0);
+    // The gather warps wait for the last MMA on the mbarrier; the warps that gathered nothing have been parked on a
+    // hardware named barrier since the start of the main loop (a spinning mbarrier wait re-issues try_wait + branch
+    // every ~18 cycles on the scheduler it shares with a gather warp: ncu counted 54 % of the kernel's executed warp
+    // instructions as barrier polls) and are released by the gather warps' arrival.
+    if (warp < p.sa) {
+      mbar_wait(accum_bar, 0);
+      tc_fence_before();
+    }
+    asm volatile("bar.sync 5, %0;" ::"n"(kEpiWarps * 32) : "memory");      // (ids 1-4: the quarter pairs of the LayerNorm epilogue)
     tc_fence_after();
     const int quarter = warp & 3;                       // TMEM lanes [32 q, 32 q + 32) are visible to warps q and q + 4
     const bool pair_sum = (p.flags & 2) != 0;           // residual rows hold 2*cout channels; add r[2c] + r[2c+1] after the ReLU
