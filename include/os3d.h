@@ -356,6 +356,13 @@ int os3d_window_attention_bf16_tc_prenorm(const void *q, const void *k, const vo
                                           int heads, int dp, const int32_t *order, const int32_t *pos_seg,
                                           const int32_t *level_info, const float *tau, float tau_min, void *out,
                                           int64_t ldo, void *stream);
+/* the training forward of the same kernel: q / k pre-normalised, attention dropout (0 <= drop_p < 1) applied to the
+ * normalised weights with the keep mask of os3d_window_attention (a hash of seed, head, query row, key row), which
+ * os3d_window_attention_bwd regenerates from the same seed. */
+int os3d_window_attention_bf16_tc_drop(const void *q, const void *k, const void *v, int64_t ld, int64_t ldv, int64_t m,
+                                       int heads, int dp, const int32_t *order, const int32_t *pos_seg,
+                                       const int32_t *level_info, const float *tau, float tau_min, float drop_p,
+                                       uint64_t seed, void *out, int64_t ldo, void *stream);
 
 /* Second tensor-core design of the same attention (attention_v2.cu): one CTA per (128-query tile, group of heads whose
  * slices make 96-128 columns), dedicated loader / MMA-issuer / softmax warps with mbarrier hand-offs, whole row slices

@@ -76,6 +76,7 @@ SIGNATURES = {
                              PTR, PTR],
     'os3d_window_attention_bf16_tc': [PTR, PTR, PTR, I64, I64, I64, I32, I32, PTR, PTR, PTR, PTR, F32, PTR, I64, PTR],
     'os3d_window_attention_bf16_tc_prenorm': [PTR, PTR, PTR, I64, I64, I64, I32, I32, PTR, PTR, PTR, PTR, F32, PTR, I64, PTR],
+    'os3d_window_attention_bf16_tc_drop': [PTR, PTR, PTR, I64, I64, I64, I32, I32, PTR, PTR, PTR, PTR, F32, F32, ctypes.c_uint64, PTR, I64, PTR],
     'os3d_window_attention_bf16_v2': [PTR, PTR, PTR, I64, I64, I64, I32, I32, PTR, PTR, PTR, PTR, F32, PTR, I64, PTR],
     'os3d_pos_embed': [PTR, I64, I32, I32, I32, I32, F32, I32, PTR, PTR],
     'os3d_voxel_majority_labels': [PTR, PTR, I64, I64, I32, PTR, PTR, PTR, PTR],
@@ -136,7 +137,7 @@ KERNELS_PER_CALL = {
     'os3d_hash_build': 1, 'os3d_subm_table': 1, 'os3d_strided_sites': 4, 'os3d_strided_tables': 2,
     'os3d_spconv_fwd_f32': 1, 'os3d_spconv_fwd_bf16': 1, 'os3d_spconv_fwd_bf16_ld': 1, 'os3d_pack_weight_f32': 1, 'os3d_pack_weight_bf16': 1, 'os3d_kernel_map_tiles': 1, 'os3d_kernel_map_order': 2, 'os3d_linear_bf16': 1, 'os3d_linear_tc_bf16': 1, 'os3d_pack_linear_bf16': 1, 'os3d_mlp_chain_bf16': 1, 'os3d_swformer_mlp_bf16': 1,
     'os3d_window_partition': 7, 'os3d_group_partition': 7, 'os3d_pos_embed': 1, 'os3d_qk_normalize': 1,
-    'os3d_window_attention': 1, 'os3d_window_attention_bwd': 2, 'os3d_window_attention_bf16_tc': 1, 'os3d_window_attention_bf16_v2': 1, 'os3d_window_attention_bf16_tc_prenorm': 1, 'os3d_wide_linear_bf16': 1, 'os3d_voxel_majority_labels': 2, 'os3d_argmax_rows': 1, 'os3d_layernorm_residual': 1,
+    'os3d_window_attention': 1, 'os3d_window_attention_bwd': 2, 'os3d_window_attention_bf16_tc': 1, 'os3d_window_attention_bf16_v2': 1, 'os3d_window_attention_bf16_tc_prenorm': 1, 'os3d_window_attention_bf16_tc_drop': 1, 'os3d_wide_linear_bf16': 1, 'os3d_voxel_majority_labels': 2, 'os3d_argmax_rows': 1, 'os3d_layernorm_residual': 1,
 }
 _launches = 0
 PROFILE = None      # bench.py sets this to a list to collect (name, start_event, end_event, work) per call

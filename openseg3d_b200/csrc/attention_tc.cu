@@ -42,6 +42,8 @@ struct Params {
   float tau_min;
   __nv_bfloat16 *out;
   int heads;
+  float drop_p;                           // DROP = 1: attention dropout (training), keep mask = hash(seed, head, query row, key row)
+  uint64_t seed;
 };
 
 __device__ __forceinline__ float ex2_ftz(float x) {
@@ -89,7 +91,10 @@ __device__ __forceinline__ uint32_t core_off(int r, int c, int sbo) { return (r 
 // is a plain copy -- the per-(tile, head) re-normalisation of every key was ~20 % of the kernel's instructions.
 // (A variant with a fifth, MMA-issuing warp and mbarrier hand-offs was built and measured in round 1 and superseded by
 // attention_v2.cu in round 2; both lose to this block-synchronous kernel at 4-7 CTAs per SM: DESIGN.md 3.2.)
-template <int DP, int KB, int PRENORM = 0>
+// DROP = 1 (training forward): the probabilities that reach MMA 2 are multiplied by the keep mask of attention.cu's
+// drop_keep() -- the same hash of (seed, head, query row, key row), so os3d_window_attention_bwd regenerates it -- while the
+// softmax denominator stays undropped (cosine_msa.py:173-174: dropout acts on the normalised weights).
+template <int DP, int KB, int PRENORM = 0, int DROP = 0>
 __global__ void __launch_bounds__(kThreads, KB == 32 ? OS3D_ATTN_CTAS : (DP <= 32 ? 4 : 3))
     window_attention_tc_kernel(const Params p) {
   constexpr int kBlockKeys = KB;
@@ -110,7 +115,8 @@ __global__ void __launch_bounds__(kThreads, KB == 32 ? OS3D_ATTN_CTAS : (DP <= 3
   __shared__ __align__(128) uint8_t p_s[kPBytes];         // !kPT only
   __shared__ __align__(8) uint64_t bars[2];               // MMA 1 done, MMA 2 done
   __shared__ uint32_t tmem_slot;
-  __shared__ uint32_t lanes_off[4];                       // per warp: 0xffffffff when its rows sit out MMA 2 of this block
+  __shared__ uint32_t lanes_off[4];
+  __shared__ int32_t krow_s[DROP ? KB : 1];               // DROP: voxel row of each key of the block                       // per warp: 0xffffffff when its rows sit out MMA 2 of this block
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   // heads of one query tile are adjacent in launch order: they run at the same time and share the q / k / v rows (each
@@ -208,6 +214,8 @@ __global__ void __launch_bounds__(kThreads, KB == 32 ? OS3D_ATTN_CTAS : (DP <= 3
 
   float m_run = -INFINITY, l_run = 0.0f;
   uint32_t ph1 = 0, ph2 = 0;
+  const float keep_scale = DROP ? 1.0f / (1.0f - p.drop_p) : 1.0f;
+  const uint64_t drop_base = p.seed ^ ((uint64_t)(uint32_t)qrow << 32) ^ ((uint64_t)h * 0x9e3779b97f4a7c15ULL);
 
   // Two threads per key; both read the whole K slice (the norm needs it), each stores the chunks c with (c & 1) == half
   // and transposes the same chunks of V.  The raw slices of block b+1 are fetched into registers while block b is in
@@ -219,13 +227,14 @@ __global__ void __launch_bounds__(kThreads, KB == 32 ? OS3D_ATTN_CTAS : (DP <= 3
   // the voxel row of this thread's key is requested TWO blocks ahead, the K / V slices one block ahead: the dependent pair
   // (order -> row -> slice) was one L2 round trip too long for a one-block lookahead (ncu: long-scoreboard stalls on the
   // slice address, and block-wide barrier stalls behind the gathering warps)
-  int32_t krow_ahead = -1;
+  int32_t krow_ahead = -1, krow_cur = -1;
   auto fetch_row = [&](int blk) {
     const int kp = ks + blk * kBlockKeys + key;
     krow_ahead = (blk < n_blocks && kp < ke && key < kBlockKeys) ? __ldg(p.order + kp) : -1;
   };
   auto prefetch = [&](int blk) {
     const int32_t krow = krow_ahead;                       // fetched by fetch_row(blk) one block earlier
+    krow_cur = krow;
     k_ok_next = krow >= 0;
     fetch_row(blk + 1);
     if (k_ok_next) {
@@ -298,6 +307,7 @@ __global__ void __launch_bounds__(kThreads, KB == 32 ? OS3D_ATTN_CTAS : (DP <= 3
         *reinterpret_cast<uint4 *>(v_s + c * kSboV + (key >> 3) * kLbo + (key & 7) * 16) = u;
       }
     }
+    if (DROP && key < kBlockKeys && half == 0) krow_s[key] = krow_cur;
     fence_proxy_async();
     tc_fence_before();
     __syncthreads();
@@ -375,14 +385,22 @@ __global__ void __launch_bounds__(kThreads, KB == 32 ? OS3D_ATTN_CTAS : (DP <= 3
     // packed bf16 pairs (one tcgen05.st) as soon as it is done.
     const uint64_t sc2 = pack2(scale, scale), ng2 = pack2(neg_ms, neg_ms);
     uint64_t l2 = pack2(0.0f, 0.0f);
+    auto keep_of = [&](int32_t krow) -> float {               // drop_keep() of attention.cu, bit for bit
+      const uint64_t x = mix64(drop_base ^ (uint64_t)(uint32_t)krow);
+      return (float)(x >> 40) * (1.0f / 16777216.0f) >= p.drop_p ? keep_scale : 0.0f;
+    };
 #pragma unroll
     for (int g = 0; g < kBlockKeys; g += 32) {
 #pragma unroll
       for (int j = 0; j < 32; j += 2) {
         float x0, x1;
         unpack2(ffma2(pack2(s[g + j], s[g + j + 1]), sc2, ng2), x0, x1);
-        const float a = ex2_ftz(x0), b = ex2_ftz(x1);
-        l2 = fadd2(l2, pack2(a, b));
+        float a = ex2_ftz(x0), b = ex2_ftz(x1);
+        l2 = fadd2(l2, pack2(a, b));                                  // the denominator ignores dropout
+        if constexpr (DROP) {
+          a *= keep_of(krow_s[g + j]);
+          b *= keep_of(krow_s[g + j + 1]);
+        }
         const __nv_bfloat162 hh = __floats2bfloat162_rn(a, b);
         pk[(g + j) >> 1] = *reinterpret_cast<const uint32_t *>(&hh);
       }
@@ -481,7 +499,8 @@ using namespace os3d;
 
 static int launch_attn_tc(const void *q, const void *k, const void *v, int64_t ld, int64_t ldv, int64_t m, int heads, int dp,
                           const int32_t *order, const int32_t *pos_seg, const int32_t *level_info, const float *tau,
-                          float tau_min, void *out, int64_t ldo, void *stream, int prenorm) {
+                          float tau_min, void *out, int64_t ldo, void *stream, int prenorm, float drop_p = 0.0f,
+                          uint64_t seed = 0) {
   if (m == 0) return 0;
   if (heads <= 0 || (dp != 16 && dp != 32 && dp != 48) || ld % 8 || ldv % 8 || ldo % 8) return OS3D_ERR_BAD_ARG;
   attn_tc::Params p;
@@ -496,11 +515,19 @@ static int launch_attn_tc(const void *q, const void *k, const void *v, int64_t l
   p.tau_min = tau_min;
   p.out = (__nv_bfloat16 *)out;
   p.heads = heads;
+  p.drop_p = drop_p;
+  p.seed = seed;
   dim3 grid((unsigned)(cdiv(m, attn_tc::kTileQ) * heads));
   cudaStream_t st = (cudaStream_t)stream;
   const char *e = getenv("OS3D_ATTN_KB");                       // tuning override: keys per block for dp = 16
   const bool kb32 = e ? atoi(e) != 64 : true;
-  if (prenorm) {
+  if (drop_p > 0.0f) {
+    if (!prenorm || drop_p >= 1.0f) return OS3D_ERR_BAD_ARG;
+    if (dp == 16 && kb32) attn_tc::window_attention_tc_kernel<16, 32, 1, 1><<<grid, attn_tc::kThreads, 0, st>>>(p);
+    else if (dp == 16) attn_tc::window_attention_tc_kernel<16, 64, 1, 1><<<grid, attn_tc::kThreads, 0, st>>>(p);
+    else if (dp == 32) attn_tc::window_attention_tc_kernel<32, 64, 1, 1><<<grid, attn_tc::kThreads, 0, st>>>(p);
+    else attn_tc::window_attention_tc_kernel<48, 64, 1, 1><<<grid, attn_tc::kThreads, 0, st>>>(p);
+  } else if (prenorm) {
     // (32 keys per block was also measured for dp = 32: 0.95 ms against 0.69 ms per level-3 layer with 64)
     if (dp == 16 && kb32) attn_tc::window_attention_tc_kernel<16, 32, 1><<<grid, attn_tc::kThreads, 0, st>>>(p);
     else if (dp == 16) attn_tc::window_attention_tc_kernel<16, 64, 1><<<grid, attn_tc::kThreads, 0, st>>>(p);
@@ -528,4 +555,15 @@ extern "C" int os3d_window_attention_bf16_tc_prenorm(const void *q, const void *
                                                      const int32_t *pos_seg, const int32_t *level_info, const float *tau,
                                                      float tau_min, void *out, int64_t ldo, void *stream) {
   return launch_attn_tc(q, k, v, ld, ldv, m, heads, dp, order, pos_seg, level_info, tau, tau_min, out, ldo, stream, 1);
+}
+
+// training forward: q / k pre-normalised, attention dropout with the keep mask os3d_window_attention_bwd regenerates
+extern "C" int os3d_window_attention_bf16_tc_drop(const void *q, const void *k, const void *v, int64_t ld, int64_t ldv,
+                                                  int64_t m, int heads, int dp, const int32_t *order,
+                                                  const int32_t *pos_seg, const int32_t *level_info, const float *tau,
+                                                  float tau_min, float drop_p, uint64_t seed, void *out, int64_t ldo,
+                                                  void *stream) {
+  if (drop_p < 0.0f || drop_p >= 1.0f) return OS3D_ERR_BAD_ARG;
+  return launch_attn_tc(q, k, v, ld, ldv, m, heads, dp, order, pos_seg, level_info, tau, tau_min, out, ldo, stream, 1, drop_p,
+                        seed);
 }

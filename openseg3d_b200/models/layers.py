@@ -27,6 +27,7 @@ _MLP_MODE = os.environ.get('OS3D_MLP_CHAIN', '1')
 _QKV_MODE = os.environ.get('OS3D_QKV', '1')             # '0': in-projections as library GEMMs + separate table add (A-B runs)
 # 'v1' (default): attention_tc.cu, one CTA per (128-query tile, head), 4-8 CTAs per SM.  'v2': attention_v2.cu, the
 # warp-specialised all-heads-per-CTA design -- parity-tested, but measured slower at levels 1-2
+_TRAIN_CKPT = os.environ.get('OS3D_TRAIN_CHECKPOINT', '1') != '0'   # 0: keep activations (180 GB of HBM) instead of recomputing each layer
 _TRAIN_TC = os.environ.get('OS3D_TRAIN_ATTN_TC', '1') != '0'      # training forward on the tensor-core kernel (bf16, no dropout)
 _ATTN_IMPL = os.environ.get('OS3D_ATTN', 'v1')
 
@@ -366,8 +367,8 @@ class _WindowAttentionFunction(torch.autograd.Function):
         tau32 = tau.detach().float().reshape(1).contiguous()
         d = c // heads
         dp = (d + 15) // 16 * 16
-        if qn.dtype == torch.bfloat16 and drop_p == 0 and dp <= 48 and m > 0 and _TRAIN_TC:
-            # forward on the tensor cores (os3d_window_attention_bf16_tc_prenorm): heads zero-padded to the MMA's K granule
+        if qn.dtype == torch.bfloat16 and dp <= 48 and m > 0 and _TRAIN_TC:
+            # forward on the tensor cores (os3d_window_attention_bf16_tc_drop): heads zero-padded to the MMA's K granule
             # in one buffer (the padding changes neither dot products nor norms), the padded output cut back to [M, C].
             # The backward kernel recomputes the probabilities from q / k / v and this output.
             if dp == d:
@@ -378,9 +379,9 @@ class _WindowAttentionFunction(torch.autograd.Function):
                 qkv = qkv.view(m, 3 * heads * dp)
             hd = heads * dp
             out_p = torch.empty((m, hd), dtype=qn.dtype, device=qn.device)
-            _lib.call('os3d_window_attention_bf16_tc_prenorm', qkv, _lib._Raw(qkv.data_ptr() + hd * 2),
+            _lib.call('os3d_window_attention_bf16_tc_drop', qkv, _lib._Raw(qkv.data_ptr() + hd * 2),
                       _lib._Raw(qkv.data_ptr() + 2 * hd * 2), 3 * hd, 3 * hd, m, heads, dp, seg.order, seg.pos_seg,
-                      seg.level_info, tau32, float(tau_min), out_p, hd)
+                      seg.level_info, tau32, float(tau_min), float(drop_p), int(seed), out_p, hd)
             out = out_p if dp == d else out_p.view(m, heads, dp)[:, :, :d].reshape(m, c)
         else:
             out = torch.empty_like(qn)
@@ -847,7 +848,7 @@ class SWFormerBlock(nn.Module):
         layer runs under torch.utils.checkpoint -- only its input is kept, the layer is recomputed in the backward (the
         attention dropout mask is regenerated from its saved seed, torch's RNG state is restored for DropPath)."""
         x = batch_dict['voxel_features']
-        ckpt = using_checkpoint and self.training and torch.is_grad_enabled()
+        ckpt = using_checkpoint and self.training and torch.is_grad_enabled() and _TRAIN_CKPT
         for i, layer in enumerate(self.layers):
             s = 0 if i < int(self.depth / 2) else 1
             args = (batch_dict[f'pos_dict_shift{s}'], batch_dict[f'flat2win_inds_shift{s}'], batch_dict[f'key_mask_shift{s}'])

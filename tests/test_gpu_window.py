@@ -222,3 +222,48 @@ def test_partition_refuses_configurations_that_drop_tokens():
     ok = SparseWindowPartitionLayer({0: {'max_tokens': 800, 'batching_range': (0, 100000)}}, (10, 10, 8), (100, 100, 16))
     assert not ok._may_drop and layer._may_drop
     ok(x)
+
+
+@pytest.mark.parametrize('c,drop_p', [(48, 0.1), (96, 0.3), (192, 0.1), (384, 0.1), (96, 0.0)])
+def test_training_forward_tensor_core_matches_simt_with_dropout(c, drop_p, monkeypatch):
+    """Training forward (cosine_msa.py:173-174, attention dropout on the normalised weights): the tensor-core kernel with
+    dropout against the SIMT kernel with the SAME seed -- both draw the keep mask from the same hash of (seed, head,
+    query row, key row), which the backward regenerates, so the two outputs differ only by bf16 rounding; and the
+    gradients that come back through the (shared) backward agree."""
+    from openseg3d_b200 import spconv
+    from openseg3d_b200.models import SparseWindowPartitionLayer
+    from openseg3d_b200.models import layers as lay
+    rng = np.random.default_rng(c)
+    torch.manual_seed(c)
+    binfo = {0: {'max_tokens': 16, 'batching_range': (0, 16)}, 1: {'max_tokens': 64, 'batching_range': (16, 64)},
+             2: {'max_tokens': 256, 'batching_range': (64, 256)}, 3: {'max_tokens': 800, 'batching_range': (256, 100000)}}
+    dense = rng.integers(0, [8, 20, 20], (1500, 3))
+    sparse = rng.integers(0, [16, 200, 200], (3000, 3))
+    cc = np.unique(np.concatenate([dense, sparse]), axis=0)
+    cc = cc[rng.permutation(len(cc))]
+    coords = torch.from_numpy(np.pad(cc, ((0, 0), (1, 0)), constant_values=0).astype(np.int32)).cuda()
+    m, heads = coords.shape[0], 8
+    layer = SparseWindowPartitionLayer(binfo, (10, 10, 8), (200, 200, 16))
+    info = layer(spconv.SparseConvTensor(torch.zeros(m, 1).cuda(), coords, [16, 200, 200], 1))
+    seg = info['flat2win_inds_shift0']['segments']
+    d = c // heads
+    q = torch.nn.functional.normalize(torch.randn(m, heads, d), dim=-1).reshape(m, c).bfloat16().cuda()
+    k = torch.nn.functional.normalize(torch.randn(m, heads, d), dim=-1).reshape(m, c).bfloat16().cuda()
+    v = torch.randn(m, c).bfloat16().cuda()
+    tau = torch.full((1, 1, 1), 0.2).cuda()
+    gout = torch.randn(m, c).bfloat16().cuda()
+    res = {}
+    for use_tc in (True, False):
+        monkeypatch.setattr(lay, '_TRAIN_TC', use_tc)
+        qq, kk, vv = [t.clone().requires_grad_(True) for t in (q, k, v)]
+        out = lay._WindowAttentionFunction.apply(qq, kk, vv, tau, 0.01, heads, seg, drop_p, 12345)
+        out.backward(gout)
+        res[use_tc] = (out.detach().float(), qq.grad.float(), kk.grad.float(), vv.grad.float())
+    scale = res[False][0].abs().max().item()
+    assert (res[True][0] - res[False][0]).abs().max().item() < 2e-2 * scale
+    if drop_p > 0:                                   # dropout really acts: the undropped output differs
+        monkeypatch.setattr(lay, '_TRAIN_TC', True)
+        plain = lay._WindowAttentionFunction.apply(q, k, v, tau, 0.01, heads, seg, 0.0, 0).float()
+        assert (plain - res[True][0]).abs().max().item() > 5e-2 * scale
+    for a, b in zip(res[True][1:], res[False][1:]):   # the backward recomputes P from q / k / v / out: out differs by bf16 rounding
+        assert (a - b).abs().max().item() < 4e-2 * b.abs().max().item()
