@@ -94,11 +94,16 @@ __device__ __forceinline__ uint32_t core_off(int r, int c, int sbo) { return (r 
 // DROP = 1 (training forward): the probabilities that reach MMA 2 are multiplied by the keep mask of attention.cu's
 // drop_keep() -- the same hash of (seed, head, query row, key row), so os3d_window_attention_bwd regenerates it -- while the
 // softmax denominator stays undropped (cosine_msa.py:173-174: dropout acts on the normalised weights).
-template <int DP, int KB, int PRENORM = 0, int DROP = 0>
-__global__ void __launch_bounds__(kThreads, KB == 32 ? OS3D_ATTN_CTAS : (DP <= 32 ? 4 : 3))
+// HP = 2 (dp = 16, 32-key blocks): two adjacent heads per CTA.  One gather of 64-byte row slices feeds both heads, the key
+// rows / window masks / barriers of a block are shared, and both heads' MMAs go out under one commit: the per-(tile, head)
+// fixed work -- two thirds of the instructions of the one-head kernel at levels 1-2 -- is paid once per pair.
+template <int DP, int KB, int PRENORM = 0, int DROP = 0, int HP = 1>
+__global__ void __launch_bounds__(kThreads, HP == 2 ? 4 : (KB == 32 ? OS3D_ATTN_CTAS : (DP <= 32 ? 4 : 3)))
     window_attention_tc_kernel(const Params p) {
   constexpr int kBlockKeys = KB;
-  constexpr int kTmemCols = (KB + DP) <= 64 ? 64 : 128;
+  static_assert(HP == 1 || (HP == 2 && PRENORM && KB == 32), "two heads per CTA: pre-normalised q / k, 32-key blocks");
+  constexpr int kTmemCols = HP * (KB + DP) <= 64 ? 64 : 128;
+  constexpr int kOCol = HP * KB;                          // S of head hh in columns [hh KB, hh KB + KB), O in [kOCol + hh DP, ...)
   constexpr int kChunks = DP / 8;                         // 16-byte chunks per head slice
   constexpr int kSboQ = kChunks * kLbo + 16;              // +16: stagger 8-row groups across banks
   constexpr bool kPT = KB == 64;                          // P in tensor memory
@@ -109,10 +114,10 @@ __global__ void __launch_bounds__(kThreads, KB == 32 ? OS3D_ATTN_CTAS : (DP <= 3
   constexpr int kVBytes = (DP / 8) * kSboV;
   constexpr int kPBytes = kPT ? 16 : (kTileQ / 8) * kSboP;
 
-  __shared__ __align__(128) uint8_t q_s[kQBytes];
-  __shared__ __align__(128) uint8_t k_s[kKBytes];         // (double-buffering K / V to move the MMA-2 wait behind the
-  __shared__ __align__(128) uint8_t v_s[kVBytes];         //  gather was measured: no gain at any level)
-  __shared__ __align__(128) uint8_t p_s[kPBytes];         // !kPT only
+  __shared__ __align__(128) uint8_t q_s[HP][kQBytes];
+  __shared__ __align__(128) uint8_t k_s[HP][kKBytes];         // (double-buffering K / V to move the MMA-2 wait behind the
+  __shared__ __align__(128) uint8_t v_s[HP][kVBytes];         //  gather was measured: no gain at any level)
+  __shared__ __align__(128) uint8_t p_s[HP][kPBytes];         // !kPT only
   __shared__ __align__(8) uint64_t bars[2];               // MMA 1 done, MMA 2 done
   __shared__ uint32_t tmem_slot;
   __shared__ uint32_t lanes_off[4];
@@ -122,9 +127,9 @@ __global__ void __launch_bounds__(kThreads, KB == 32 ? OS3D_ATTN_CTAS : (DP <= 3
   // heads of one query tile are adjacent in launch order: they run at the same time and share the q / k / v rows (each
   // head reads a 32-96 byte slice of the same lines) while those are still in L2.  With heads on the slow grid axis
   // every line came from HBM once per head (ncu: 3.1 GB of DRAM reads per launch for 0.7 GB of q / k / v).
-  const int h = blockIdx.x % p.heads;
+  const int h = (blockIdx.x % (p.heads / HP)) * HP;       // first head of this CTA
   const int n_tok = __ldg(p.level_info + 14);
-  const int p0 = (blockIdx.x / p.heads) * kTileQ;
+  const int p0 = (blockIdx.x / (p.heads / HP)) * kTileQ;
   if (p0 >= n_tok) return;
   const int p_last = min(p0 + kTileQ, n_tok) - 1;
 
@@ -148,10 +153,12 @@ __global__ void __launch_bounds__(kThreads, KB == 32 ? OS3D_ATTN_CTAS : (DP <= 3
     qrow = __ldg(p.order + qp);
   }
   if (PRENORM) {
-    const uint4 *src = reinterpret_cast<const uint4 *>(p.q + (int64_t)qrow * p.ld + h * DP);
+    const uint4 *src = reinterpret_cast<const uint4 *>(p.q + (int64_t)qrow * p.ld + h * DP);     // HP heads: one contiguous slice
 #pragma unroll
-    for (int c = 0; c < kChunks; ++c)
-      *reinterpret_cast<uint4 *>(q_s + core_off(tid, c, kSboQ)) = q_ok ? __ldg(src + c) : make_uint4(0, 0, 0, 0);
+    for (int hh = 0; hh < HP; ++hh)
+#pragma unroll
+      for (int c = 0; c < kChunks; ++c)
+        *reinterpret_cast<uint4 *>(q_s[hh] + core_off(tid, c, kSboQ)) = q_ok ? __ldg(src + hh * kChunks + c) : make_uint4(0, 0, 0, 0);
   } else {
     float f[DP];
     if (q_ok) {
@@ -184,7 +191,7 @@ __global__ void __launch_bounds__(kThreads, KB == 32 ? OS3D_ATTN_CTAS : (DP <= 3
         const __nv_bfloat162 hh = __floats2bfloat162_rn(f[c * 8 + 2 * i], f[c * 8 + 2 * i + 1]);
         w[i] = *reinterpret_cast<const uint32_t *>(&hh);
       }
-      *reinterpret_cast<uint4 *>(q_s + core_off(tid, c, kSboQ)) = make_uint4(w[0], w[1], w[2], w[3]);
+      *reinterpret_cast<uint4 *>(q_s[0] + core_off(tid, c, kSboQ)) = make_uint4(w[0], w[1], w[2], w[3]);
     }
   }
 
@@ -208,19 +215,22 @@ __global__ void __launch_bounds__(kThreads, KB == 32 ? OS3D_ATTN_CTAS : (DP <= 3
 #pragma unroll
     for (int i = 0; i < 16; ++i) z[i] = 0u;
 #pragma unroll
-    for (int c0 = 0; c0 < DP; c0 += 16) tmem_st16(tmem_row + kBlockKeys + c0, z);
+    for (int c0 = 0; c0 < HP * DP; c0 += 16) tmem_st16(tmem_row + kOCol + c0, z);
     tmem_st_wait();
   }
 
-  float m_run = -INFINITY, l_run = 0.0f;
+  float m_run[HP], l_run[HP];
+#pragma unroll
+  for (int hh = 0; hh < HP; ++hh) { m_run[hh] = -INFINITY; l_run[hh] = 0.0f; }
   uint32_t ph1 = 0, ph2 = 0;
   const float keep_scale = DROP ? 1.0f / (1.0f - p.drop_p) : 1.0f;
-  const uint64_t drop_base = p.seed ^ ((uint64_t)(uint32_t)qrow << 32) ^ ((uint64_t)h * 0x9e3779b97f4a7c15ULL);
+  const uint64_t drop_row = p.seed ^ ((uint64_t)(uint32_t)qrow << 32);
 
   // Two threads per key; both read the whole K slice (the norm needs it), each stores the chunks c with (c & 1) == half
   // and transposes the same chunks of V.  The raw slices of block b+1 are fetched into registers while block b is in
   // its MMA / softmax phases, so the two dependent global loads (order -> row) are off the critical path.
-  const int key = tid >> 1, half = tid & 1;              // KB = 32: threads 64..127 have no key (k_ok_next stays false)
+  // (one head, KB = 32: threads 64..127 have no key and k_ok_next stays false; two heads: thread pairs 2 key + hh)
+  const int key = tid / (2 * HP), half = tid & 1, hk = (tid >> 1) % HP;       // hk: which of the CTA's heads this thread gathers
   constexpr int kVChunks = (kChunks + 1) / 2;
   uint4 k_raw[kChunks], v_raw[kVChunks];
   bool k_ok_next = false;
@@ -238,8 +248,8 @@ __global__ void __launch_bounds__(kThreads, KB == 32 ? OS3D_ATTN_CTAS : (DP <= 3
     k_ok_next = krow >= 0;
     fetch_row(blk + 1);
     if (k_ok_next) {
-      const uint4 *ksrc = reinterpret_cast<const uint4 *>(p.k + (int64_t)krow * p.ld + h * DP);
-      const uint4 *vsrc = reinterpret_cast<const uint4 *>(p.v + (int64_t)krow * p.ldv + h * DP);
+      const uint4 *ksrc = reinterpret_cast<const uint4 *>(p.k + (int64_t)krow * p.ld + (h + hk) * DP);
+      const uint4 *vsrc = reinterpret_cast<const uint4 *>(p.v + (int64_t)krow * p.ldv + (h + hk) * DP);
 #pragma unroll
       for (int c = 0; c < kChunks; ++c)
         if (!PRENORM || (c & 1) == half) k_raw[c] = __ldg(ksrc + c);      // PRENORM: only the chunks this thread stores
@@ -262,7 +272,7 @@ __global__ void __launch_bounds__(kThreads, KB == 32 ? OS3D_ATTN_CTAS : (DP <= 3
 #pragma unroll
       for (int c = 0; c < kChunks; ++c) {
         if ((c & 1) != half) continue;
-        *reinterpret_cast<uint4 *>(k_s + core_off(key, c, kSboQ)) = k_ok_next ? k_raw[c] : make_uint4(0, 0, 0, 0);
+        *reinterpret_cast<uint4 *>(k_s[hk] + core_off(key, c, kSboQ)) = k_ok_next ? k_raw[c] : make_uint4(0, 0, 0, 0);
       }
     } else if (key < kBlockKeys) {
       float f[DP];
@@ -290,7 +300,7 @@ __global__ void __launch_bounds__(kThreads, KB == 32 ? OS3D_ATTN_CTAS : (DP <= 3
           const __nv_bfloat162 hh = __floats2bfloat162_rn(f[c * 8 + 2 * i] * inv, f[c * 8 + 2 * i + 1] * inv);
           w[i] = *reinterpret_cast<const uint32_t *>(&hh);
         }
-        *reinterpret_cast<uint4 *>(k_s + core_off(key, c, kSboQ)) = make_uint4(w[0], w[1], w[2], w[3]);
+        *reinterpret_cast<uint4 *>(k_s[hk] + core_off(key, c, kSboQ)) = make_uint4(w[0], w[1], w[2], w[3]);
       }
     }
     if (key < kBlockKeys) {
@@ -304,19 +314,21 @@ __global__ void __launch_bounds__(kThreads, KB == 32 ? OS3D_ATTN_CTAS : (DP <= 3
         const int c = 2 * cv + half;
         if (c >= kChunks) continue;
         const uint4 u = k_ok_next ? v_raw[cv] : make_uint4(0, 0, 0, 0);
-        *reinterpret_cast<uint4 *>(v_s + c * kSboV + (key >> 3) * kLbo + (key & 7) * 16) = u;
+        *reinterpret_cast<uint4 *>(v_s[hk] + c * kSboV + (key >> 3) * kLbo + (key & 7) * 16) = u;
       }
     }
-    if (DROP && key < kBlockKeys && half == 0) krow_s[key] = krow_cur;
+    if (DROP && key < kBlockKeys && half == 0 && hk == 0) krow_s[key] = krow_cur;
     fence_proxy_async();
     tc_fence_before();
     __syncthreads();
     if (tid == 0) {
       tc_fence_after();
 #pragma unroll
-      for (int s = 0; s < DP / 16; ++s)
-        umma_bf16(tmem_base, make_kmajor_nosw_desc(smem_u32(q_s) + s * 2 * kLbo, kLbo, kSboQ),
-                  make_kmajor_nosw_desc(smem_u32(k_s) + s * 2 * kLbo, kLbo, kSboQ), idesc1, s > 0 ? 1u : 0u);
+      for (int hh = 0; hh < HP; ++hh)
+#pragma unroll
+        for (int s = 0; s < DP / 16; ++s)
+          umma_bf16(tmem_base + hh * kBlockKeys, make_kmajor_nosw_desc(smem_u32(q_s[hh]) + s * 2 * kLbo, kLbo, kSboQ),
+                    make_kmajor_nosw_desc(smem_u32(k_s[hh]) + s * 2 * kLbo, kLbo, kSboQ), idesc1, s > 0 ? 1u : 0u);
       umma_commit(bar1);
     }
     prefetch(blk + 1);        // global loads for the next key block fly during MMA 1, the softmax and MMA 2
@@ -333,33 +345,36 @@ __global__ void __launch_bounds__(kThreads, KB == 32 ? OS3D_ATTN_CTAS : (DP <= 3
     // are folded into one FFMA feeding ex2.approx.ftz (masked scores are -inf -> probability exactly 0)
     const uint64_t valid = hi > lo ? ((~0ull >> (64 - (hi - lo))) << lo) : 0ull;
     const uint32_t v_lo = (uint32_t)valid, v_hi = (uint32_t)(valid >> 32);
-    float alpha = 1.0f;
-    uint32_t pk[kBlockKeys / 2];                            // the row of probabilities, packed bf16 pairs
     // Windows are short, so most (warp, key block) pairs are entirely off the block diagonal: one vote skips the TMEM
     // load, the whole softmax and the P store for them, and takes their rows out of MMA 2.
     const bool warp_has_keys = __any_sync(0xffffffffu, valid != 0ull);
     if (kPT && lane == 0) lanes_off[warp] = warp_has_keys ? 0u : 0xffffffffu;
-    if (warp_has_keys) {
     // q and k are unit vectors, so a raw score never exceeds 1 (+ bf16 rounding): with a moderate temperature the
     // softmax can use the FIXED reference maximum 1 -- no running maximum, no FMNMX per score, no rescaling of O --
     // and cannot underflow (2 * scale <= 120 binades).  Small temperatures keep the online maximum.
     const uint64_t full_mask = kBlockKeys == 64 ? ~0ull : ((1ull << (kBlockKeys & 63)) - 1ull);
     const bool all_valid = __all_sync(0xffffffffu, valid == full_mask);
+#pragma unroll
+    for (int hh = 0; hh < HP; ++hh) {                       // the heads of this CTA share the block's masks and key rows
+    float alpha = 1.0f;
+    uint32_t pk[kBlockKeys / 2];                            // the row of probabilities, packed bf16 pairs
+    const uint32_t s_col = tmem_row + hh * kBlockKeys, o_col = tmem_row + kOCol + hh * DP;
+    if (warp_has_keys) {
     float s[kBlockKeys];
     {
       uint32_t r[32];
-      tmem_ld32(tmem_row, r);
+      tmem_ld32(s_col, r);
       tmem_ld_wait();
 #pragma unroll
       for (int i = 0; i < 32; ++i) s[i] = __uint_as_float(r[i]);
       if constexpr (kBlockKeys == 64) {
-        tmem_ld32(tmem_row + 32, r);
+        tmem_ld32(s_col + 32, r);
         tmem_ld_wait();
 #pragma unroll
         for (int i = 0; i < 32; ++i) s[32 + i] = __uint_as_float(r[i]);
       }
     }
-    float m_new = m_run, neg_ms;
+    float m_new = m_run[hh], neg_ms;
     if (fixed_max) {
       if (!all_valid) {
 #pragma unroll
@@ -377,7 +392,7 @@ __global__ void __launch_bounds__(kThreads, KB == 32 ? OS3D_ATTN_CTAS : (DP <= 3
         m_new = fmaxf(m_new, s[j]);
       }
       const float m_use = (m_new == -INFINITY) ? 0.0f : m_new;    // nothing valid so far: ex2(-inf) = 0 everywhere
-      alpha = ex2_ftz((m_run - m_use) * scale);        // m_run = -inf -> 0 (l_run, O are still 0 then)
+      alpha = ex2_ftz((m_run[hh] - m_use) * scale);        // m_run = -inf -> 0 (l_run, O are still 0 then)
       neg_ms = -m_use * scale;
     }
     // two scores per instruction: FFMA2 / FADD2 (fma.rn.f32x2, add.rn.f32x2 -- the kernel is bound by its instruction
@@ -385,6 +400,7 @@ __global__ void __launch_bounds__(kThreads, KB == 32 ? OS3D_ATTN_CTAS : (DP <= 3
     // packed bf16 pairs (one tcgen05.st) as soon as it is done.
     const uint64_t sc2 = pack2(scale, scale), ng2 = pack2(neg_ms, neg_ms);
     uint64_t l2 = pack2(0.0f, 0.0f);
+    const uint64_t drop_base = drop_row ^ ((uint64_t)(h + hh) * 0x9e3779b97f4a7c15ULL);
     auto keep_of = [&](int32_t krow) -> float {               // drop_keep() of attention.cu, bit for bit
       const uint64_t x = mix64(drop_base ^ (uint64_t)(uint32_t)krow);
       return (float)(x >> 40) * (1.0f / 16777216.0f) >= p.drop_p ? keep_scale : 0.0f;
@@ -401,16 +417,16 @@ __global__ void __launch_bounds__(kThreads, KB == 32 ? OS3D_ATTN_CTAS : (DP <= 3
           a *= keep_of(krow_s[g + j]);
           b *= keep_of(krow_s[g + j + 1]);
         }
-        const __nv_bfloat162 hh = __floats2bfloat162_rn(a, b);
-        pk[(g + j) >> 1] = *reinterpret_cast<const uint32_t *>(&hh);
+        const __nv_bfloat162 ab = __floats2bfloat162_rn(a, b);
+        pk[(g + j) >> 1] = *reinterpret_cast<const uint32_t *>(&ab);
       }
-      if constexpr (kPT) tmem_st16(tmem_row + g / 2, reinterpret_cast<const uint32_t (&)[16]>(pk[g / 2]));
+      if constexpr (kPT) tmem_st16(s_col + g / 2, reinterpret_cast<const uint32_t (&)[16]>(pk[g / 2]));
     }
     float l_lo, l_hi;
     unpack2(l2, l_lo, l_hi);
     const float l_blk = l_lo + l_hi;
-    l_run = l_run * alpha + l_blk;
-    m_run = m_new;
+    l_run[hh] = l_run[hh] * alpha + l_blk;
+    m_run[hh] = m_new;
     } else if constexpr (!kPT) {
 #pragma unroll
       for (int i = 0; i < kBlockKeys / 2; ++i) pk[i] = 0u;
@@ -418,21 +434,22 @@ __global__ void __launch_bounds__(kThreads, KB == 32 ? OS3D_ATTN_CTAS : (DP <= 3
     if constexpr (!kPT) {
 #pragma unroll
       for (int c = 0; c < kBlockKeys / 8; ++c)
-        *reinterpret_cast<uint4 *>(p_s + core_off(tid, c, kSboP)) = make_uint4(pk[4 * c], pk[4 * c + 1], pk[4 * c + 2], pk[4 * c + 3]);
+        *reinterpret_cast<uint4 *>(p_s[hh] + core_off(tid, c, kSboP)) = make_uint4(pk[4 * c], pk[4 * c + 1], pk[4 * c + 2], pk[4 * c + 3]);
     }
     // rescale O if any row of this warp moved its maximum (tcgen05.ld / st are warp-collective)
     if (blk > 0 && __any_sync(0xffffffffu, alpha != 1.0f)) {
 #pragma unroll
       for (int c0 = 0; c0 < DP; c0 += 16) {
         uint32_t o[16];
-        tmem_ld16(tmem_row + kBlockKeys + c0, o);
+        tmem_ld16(o_col + c0, o);
         tmem_ld_wait();
 #pragma unroll
         for (int i = 0; i < 16; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
-        tmem_st16(tmem_row + kBlockKeys + c0, o);
+        tmem_st16(o_col + c0, o);
       }
       if constexpr (!kPT) tmem_st_wait();
     }
+    }   // heads of this CTA
     if constexpr (kPT) {
       if (warp_has_keys) tmem_st_wait();
     }
@@ -442,9 +459,11 @@ __global__ void __launch_bounds__(kThreads, KB == 32 ? OS3D_ATTN_CTAS : (DP <= 3
     if (!kPT && tid == 0) {
       tc_fence_after();
 #pragma unroll
-      for (int s2 = 0; s2 < kBlockKeys / 16; ++s2)
-        umma_bf16(tmem_base + kBlockKeys, make_kmajor_nosw_desc(smem_u32(p_s) + s2 * 2 * kLbo, kLbo, kSboP),
-                  make_kmajor_nosw_desc(smem_u32(v_s) + s2 * 2 * kLbo, kLbo, kSboV), idesc2, (blk > 0 || s2 > 0) ? 1u : 0u);
+      for (int hh = 0; hh < HP; ++hh)
+#pragma unroll
+        for (int s2 = 0; s2 < kBlockKeys / 16; ++s2)
+          umma_bf16(tmem_base + kOCol + hh * DP, make_kmajor_nosw_desc(smem_u32(p_s[hh]) + s2 * 2 * kLbo, kLbo, kSboP),
+                    make_kmajor_nosw_desc(smem_u32(v_s[hh]) + s2 * 2 * kLbo, kLbo, kSboV), idesc2, (blk > 0 || s2 > 0) ? 1u : 0u);
       umma_commit(bar2);
     }
     if (kPT && tid == 0) {
@@ -454,7 +473,7 @@ __global__ void __launch_bounds__(kThreads, KB == 32 ? OS3D_ATTN_CTAS : (DP <= 3
         const uint32_t v_hi_w = nosw_desc_hi(kSboV);
 #pragma unroll
         for (int s2 = 0; s2 < kBlockKeys / 16; ++s2)
-          umma_bf16_ts_acc(tmem_base + kBlockKeys, tmem_base + s2 * 8, nosw_desc_lo(smem_u32(v_s) + s2 * 2 * kLbo, kLbo), v_hi_w,
+          umma_bf16_ts_acc(tmem_base + kOCol, tmem_base + s2 * 8, nosw_desc_lo(smem_u32(v_s[0]) + s2 * 2 * kLbo, kLbo), v_hi_w,
                            idesc2, off0, off1, off2, off3);
       }
       umma_commit(bar2);
@@ -464,20 +483,21 @@ __global__ void __launch_bounds__(kThreads, KB == 32 ? OS3D_ATTN_CTAS : (DP <= 3
   // ---- epilogue ----
   mbar_wait(bar2, ph2);
   tc_fence_after();
-  {
-    const float inv_l = l_run > 0.0f ? 1.0f / l_run : 0.0f;
-    __nv_bfloat16 *dst = p.out + (int64_t)qrow * p.ldo + h * DP;
+#pragma unroll
+  for (int hh = 0; hh < HP; ++hh) {
+    const float inv_l = l_run[hh] > 0.0f ? 1.0f / l_run[hh] : 0.0f;
+    __nv_bfloat16 *dst = p.out + (int64_t)qrow * p.ldo + (h + hh) * DP;
 #pragma unroll
     for (int c0 = 0; c0 < DP; c0 += 16) {
       uint32_t o[16];
-      tmem_ld16(tmem_row + kBlockKeys + c0, o);
+      tmem_ld16(tmem_row + kOCol + hh * DP + c0, o);
       tmem_ld_wait();
       if (q_ok) {
         uint32_t w[8];
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
-          const __nv_bfloat162 hh = __floats2bfloat162_rn(__uint_as_float(o[2 * i]) * inv_l, __uint_as_float(o[2 * i + 1]) * inv_l);
-          w[i] = *reinterpret_cast<const uint32_t *>(&hh);
+          const __nv_bfloat162 ab = __floats2bfloat162_rn(__uint_as_float(o[2 * i]) * inv_l, __uint_as_float(o[2 * i + 1]) * inv_l);
+          w[i] = *reinterpret_cast<const uint32_t *>(&ab);
         }
         reinterpret_cast<uint4 *>(dst + c0)[0] = make_uint4(w[0], w[1], w[2], w[3]);
         reinterpret_cast<uint4 *>(dst + c0)[1] = make_uint4(w[4], w[5], w[6], w[7]);
@@ -521,15 +541,20 @@ static int launch_attn_tc(const void *q, const void *k, const void *v, int64_t l
   cudaStream_t st = (cudaStream_t)stream;
   const char *e = getenv("OS3D_ATTN_KB");                       // tuning override: keys per block for dp = 16
   const bool kb32 = e ? atoi(e) != 64 : true;
+  const char *e2 = getenv("OS3D_ATTN_HP");                      // tuning override: heads per CTA for dp = 16 (1 | 2)
+  const bool pair = dp == 16 && kb32 && prenorm && heads % 2 == 0 && (e2 ? atoi(e2) == 2 : true);
+  dim3 grid2((unsigned)(cdiv(m, attn_tc::kTileQ) * (heads / 2)));
   if (drop_p > 0.0f) {
     if (!prenorm || drop_p >= 1.0f) return OS3D_ERR_BAD_ARG;
-    if (dp == 16 && kb32) attn_tc::window_attention_tc_kernel<16, 32, 1, 1><<<grid, attn_tc::kThreads, 0, st>>>(p);
+    if (pair) attn_tc::window_attention_tc_kernel<16, 32, 1, 1, 2><<<grid2, attn_tc::kThreads, 0, st>>>(p);
+    else if (dp == 16 && kb32) attn_tc::window_attention_tc_kernel<16, 32, 1, 1><<<grid, attn_tc::kThreads, 0, st>>>(p);
     else if (dp == 16) attn_tc::window_attention_tc_kernel<16, 64, 1, 1><<<grid, attn_tc::kThreads, 0, st>>>(p);
     else if (dp == 32) attn_tc::window_attention_tc_kernel<32, 64, 1, 1><<<grid, attn_tc::kThreads, 0, st>>>(p);
     else attn_tc::window_attention_tc_kernel<48, 64, 1, 1><<<grid, attn_tc::kThreads, 0, st>>>(p);
   } else if (prenorm) {
     // (32 keys per block was also measured for dp = 32: 0.95 ms against 0.69 ms per level-3 layer with 64)
-    if (dp == 16 && kb32) attn_tc::window_attention_tc_kernel<16, 32, 1><<<grid, attn_tc::kThreads, 0, st>>>(p);
+    if (pair) attn_tc::window_attention_tc_kernel<16, 32, 1, 0, 2><<<grid2, attn_tc::kThreads, 0, st>>>(p);
+    else if (dp == 16 && kb32) attn_tc::window_attention_tc_kernel<16, 32, 1><<<grid, attn_tc::kThreads, 0, st>>>(p);
     else if (dp == 16) attn_tc::window_attention_tc_kernel<16, 64, 1><<<grid, attn_tc::kThreads, 0, st>>>(p);
     else if (dp == 32) attn_tc::window_attention_tc_kernel<32, 64, 1><<<grid, attn_tc::kThreads, 0, st>>>(p);
     else attn_tc::window_attention_tc_kernel<48, 64, 1><<<grid, attn_tc::kThreads, 0, st>>>(p);
