@@ -25,6 +25,9 @@ namespace os3d {
 namespace attn_tc {
 using namespace ptx;
 
+#ifndef OS3D_ATTN_CTAS32
+#define OS3D_ATTN_CTAS32 4       /* 5 (96 registers, S / O as two TMEM allocations) spills ~190 B: 0.87 against 0.64 ms at level 3 */
+#endif
 #ifndef OS3D_ATTN_CTAS
 #define OS3D_ATTN_CTAS 7
 #endif
@@ -98,11 +101,14 @@ __device__ __forceinline__ uint32_t core_off(int r, int c, int sbo) { return (r 
 // rows / window masks / barriers of a block are shared, and both heads' MMAs go out under one commit: the per-(tile, head)
 // fixed work -- two thirds of the instructions of the one-head kernel at levels 1-2 -- is paid once per pair.
 template <int DP, int KB, int PRENORM = 0, int DROP = 0, int HP = 1>
-__global__ void __launch_bounds__(kThreads, HP == 2 ? 4 : (KB == 32 ? OS3D_ATTN_CTAS : (DP <= 32 ? 4 : 3)))
+__global__ void __launch_bounds__(kThreads, HP == 2 ? 5 : (KB == 32 ? OS3D_ATTN_CTAS : (DP == 32 ? OS3D_ATTN_CTAS32 : (DP < 32 ? 4 : 3))))
     window_attention_tc_kernel(const Params p) {
   constexpr int kBlockKeys = KB;
   static_assert(HP == 1 || (HP == 2 && PRENORM && KB == 32), "two heads per CTA: pre-normalised q / k, 32-key blocks");
   constexpr int kTmemCols = HP * (KB + DP) <= 64 ? 64 : 128;
+  // HP = 2: the scores (64 columns) and the outputs (32) are two tensor-memory allocations -- 96 columns per CTA, five
+  // CTAs per SM -- where one power-of-two block would take 128 (four CTAs)
+  constexpr bool kSplitAlloc = HP == 2 && HP * KB == 64 && HP * DP == 32;
   constexpr int kOCol = HP * KB;                          // S of head hh in columns [hh KB, hh KB + KB), O in [kOCol + hh DP, ...)
   constexpr int kChunks = DP / 8;                         // 16-byte chunks per head slice
   constexpr int kSboQ = kChunks * kLbo + 16;              // +16: stagger 8-row groups across banks
@@ -119,7 +125,7 @@ __global__ void __launch_bounds__(kThreads, HP == 2 ? 4 : (KB == 32 ? OS3D_ATTN_
   __shared__ __align__(128) uint8_t v_s[HP][kVBytes];         //  gather was measured: no gain at any level)
   __shared__ __align__(128) uint8_t p_s[HP][kPBytes];         // !kPT only
   __shared__ __align__(8) uint64_t bars[2];               // MMA 1 done, MMA 2 done
-  __shared__ uint32_t tmem_slot;
+  __shared__ uint32_t tmem_slot, tmem_slot_o;
   __shared__ uint32_t lanes_off[4];
   __shared__ int32_t krow_s[DROP ? KB : 1];               // DROP: voxel row of each key of the block                       // per warp: 0xffffffff when its rows sit out MMA 2 of this block
 
@@ -139,7 +145,10 @@ __global__ void __launch_bounds__(kThreads, HP == 2 ? 4 : (KB == 32 ? OS3D_ATTN_
     mbar_init(bar2, 1);
     fence_barrier_init();
   }
-  if (warp == 0) tmem_alloc(smem_u32(&tmem_slot), kTmemCols);
+  if (warp == 0) {
+    if constexpr (kSplitAlloc) tmem_alloc2(smem_u32(&tmem_slot), HP * KB, smem_u32(&tmem_slot_o), HP * DP);
+    else tmem_alloc(smem_u32(&tmem_slot), kTmemCols);
+  }
 
   // ---- this thread's query row ----
   const int qp = p0 + tid;
@@ -205,7 +214,8 @@ __global__ void __launch_bounds__(kThreads, HP == 2 ? 4 : (KB == 32 ? OS3D_ATTN_
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = tmem_slot;
-  const uint32_t tmem_row = tmem_base + ((uint32_t)(warp * 32) << 16);
+  const uint32_t tmem_o = kSplitAlloc ? tmem_slot_o : tmem_base + kOCol;                   // O accumulators
+  const uint32_t tmem_row = tmem_base + ((uint32_t)(warp * 32) << 16), tmem_row_o = tmem_o + ((uint32_t)(warp * 32) << 16);
   const uint32_t idesc1 = make_idesc_bf16(kTileQ, kBlockKeys), idesc2 = make_idesc_bf16(kTileQ, DP) | (1u << 16);   // bit 16: B is MN-major
   const float scale = 1.4426950408889634f / fmaxf(__ldg(p.tau), p.tau_min);
   const bool fixed_max = scale <= 60.0f;
@@ -215,7 +225,7 @@ __global__ void __launch_bounds__(kThreads, HP == 2 ? 4 : (KB == 32 ? OS3D_ATTN_
 #pragma unroll
     for (int i = 0; i < 16; ++i) z[i] = 0u;
 #pragma unroll
-    for (int c0 = 0; c0 < HP * DP; c0 += 16) tmem_st16(tmem_row + kOCol + c0, z);
+    for (int c0 = 0; c0 < HP * DP; c0 += 16) tmem_st16(tmem_row_o + c0, z);
     tmem_st_wait();
   }
 
@@ -358,7 +368,7 @@ __global__ void __launch_bounds__(kThreads, HP == 2 ? 4 : (KB == 32 ? OS3D_ATTN_
     for (int hh = 0; hh < HP; ++hh) {                       // the heads of this CTA share the block's masks and key rows
     float alpha = 1.0f;
     uint32_t pk[kBlockKeys / 2];                            // the row of probabilities, packed bf16 pairs
-    const uint32_t s_col = tmem_row + hh * kBlockKeys, o_col = tmem_row + kOCol + hh * DP;
+    const uint32_t s_col = tmem_row + hh * kBlockKeys, o_col = tmem_row_o + hh * DP;
     if (warp_has_keys) {
     float s[kBlockKeys];
     {
@@ -462,7 +472,7 @@ __global__ void __launch_bounds__(kThreads, HP == 2 ? 4 : (KB == 32 ? OS3D_ATTN_
       for (int hh = 0; hh < HP; ++hh)
 #pragma unroll
         for (int s2 = 0; s2 < kBlockKeys / 16; ++s2)
-          umma_bf16(tmem_base + kOCol + hh * DP, make_kmajor_nosw_desc(smem_u32(p_s[hh]) + s2 * 2 * kLbo, kLbo, kSboP),
+          umma_bf16(tmem_o + hh * DP, make_kmajor_nosw_desc(smem_u32(p_s[hh]) + s2 * 2 * kLbo, kLbo, kSboP),
                     make_kmajor_nosw_desc(smem_u32(v_s[hh]) + s2 * 2 * kLbo, kLbo, kSboV), idesc2, (blk > 0 || s2 > 0) ? 1u : 0u);
       umma_commit(bar2);
     }
@@ -473,7 +483,7 @@ __global__ void __launch_bounds__(kThreads, HP == 2 ? 4 : (KB == 32 ? OS3D_ATTN_
         const uint32_t v_hi_w = nosw_desc_hi(kSboV);
 #pragma unroll
         for (int s2 = 0; s2 < kBlockKeys / 16; ++s2)
-          umma_bf16_ts_acc(tmem_base + kOCol, tmem_base + s2 * 8, nosw_desc_lo(smem_u32(v_s[0]) + s2 * 2 * kLbo, kLbo), v_hi_w,
+          umma_bf16_ts_acc(tmem_o, tmem_base + s2 * 8, nosw_desc_lo(smem_u32(v_s[0]) + s2 * 2 * kLbo, kLbo), v_hi_w,
                            idesc2, off0, off1, off2, off3);
       }
       umma_commit(bar2);
@@ -490,7 +500,7 @@ __global__ void __launch_bounds__(kThreads, HP == 2 ? 4 : (KB == 32 ? OS3D_ATTN_
 #pragma unroll
     for (int c0 = 0; c0 < DP; c0 += 16) {
       uint32_t o[16];
-      tmem_ld16(tmem_row + kOCol + hh * DP + c0, o);
+      tmem_ld16(tmem_row_o + hh * DP + c0, o);
       tmem_ld_wait();
       if (q_ok) {
         uint32_t w[8];
@@ -508,7 +518,12 @@ __global__ void __launch_bounds__(kThreads, HP == 2 ? 4 : (KB == 32 ? OS3D_ATTN_
   __syncthreads();
   if (warp == 0) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, kTmemCols);
+    if constexpr (kSplitAlloc) {
+      tmem_dealloc(tmem_base, HP * KB);
+      tmem_dealloc(tmem_o, HP * DP);
+    } else {
+      tmem_dealloc(tmem_base, kTmemCols);
+    }
   }
 }
 
