@@ -26,7 +26,7 @@ namespace attn_tc {
 using namespace ptx;
 
 #ifndef OS3D_ATTN_CTAS32
-#define OS3D_ATTN_CTAS32 4       /* 5 (96 registers, S / O as two TMEM allocations) spills ~190 B: 0.87 against 0.64 ms at level 3 */
+#define OS3D_ATTN_CTAS32 4       /* 5 (96 registers, S / O as two TMEM allocations): spills, 0.64 against 0.63 ms at level 3 */
 #endif
 #ifndef OS3D_ATTN_CTAS
 #define OS3D_ATTN_CTAS 7
@@ -121,8 +121,11 @@ __global__ void __launch_bounds__(kThreads, HP == 2 ? 5 : (KB == 32 ? OS3D_ATTN_
   constexpr int kPBytes = kPT ? 16 : (kTileQ / 8) * kSboP;
 
   __shared__ __align__(128) uint8_t q_s[HP][kQBytes];
-  __shared__ __align__(128) uint8_t k_s[HP][kKBytes];         // (double-buffering K / V to move the MMA-2 wait behind the
-  __shared__ __align__(128) uint8_t v_s[HP][kVBytes];         //  gather was measured: no gain at any level)
+  // PRENORM: K / V arrive ready to use, so the gather is cp.async (LDGSTS) straight into the operand layout of the NEXT
+  // block's buffer -- no register staging (16 registers and their spills gone), no st.shared -- hence two buffers.
+  constexpr int kBufs = PRENORM ? 2 : 1;
+  __shared__ __align__(128) uint8_t k_s[kBufs][HP][kKBytes];
+  __shared__ __align__(128) uint8_t v_s[kBufs][HP][kVBytes];
   __shared__ __align__(128) uint8_t p_s[HP][kPBytes];         // !kPT only
   __shared__ __align__(8) uint64_t bars[2];               // MMA 1 done, MMA 2 done
   __shared__ uint32_t tmem_slot, tmem_slot_o;
@@ -242,7 +245,7 @@ __global__ void __launch_bounds__(kThreads, HP == 2 ? 5 : (KB == 32 ? OS3D_ATTN_
   // (one head, KB = 32: threads 64..127 have no key and k_ok_next stays false; two heads: thread pairs 2 key + hh)
   const int key = tid / (2 * HP), half = tid & 1, hk = (tid >> 1) % HP;       // hk: which of the CTA's heads this thread gathers
   constexpr int kVChunks = (kChunks + 1) / 2;
-  uint4 k_raw[kChunks], v_raw[kVChunks];
+  uint4 k_raw[PRENORM ? 1 : kChunks], v_raw[PRENORM ? 1 : kVChunks];          // !PRENORM: register staging (the norm needs the slice)
   bool k_ok_next = false;
   // the voxel row of this thread's key is requested TWO blocks ahead, the K / V slices one block ahead: the dependent pair
   // (order -> row -> slice) was one L2 round trip too long for a one-block lookahead (ncu: long-scoreboard stalls on the
@@ -257,7 +260,25 @@ __global__ void __launch_bounds__(kThreads, HP == 2 ? 5 : (KB == 32 ? OS3D_ATTN_
     krow_cur = krow;
     k_ok_next = krow >= 0;
     fetch_row(blk + 1);
-    if (k_ok_next) {
+    if constexpr (PRENORM) {
+      if (key < kBlockKeys && blk < n_blocks) {
+        const int buf = blk & 1;
+        const int32_t row = max(krow, 0);
+        const uint32_t nb = k_ok_next ? 16u : 0u;            // no key here: zero-fill (the address stays valid)
+        const uint4 *ksrc = reinterpret_cast<const uint4 *>(p.k + (int64_t)row * p.ld + (h + hk) * DP);
+        const uint4 *vsrc = reinterpret_cast<const uint4 *>(p.v + (int64_t)row * p.ldv + (h + hk) * DP);
+        const uint32_t kd = smem_u32(k_s[buf][hk]), vd = smem_u32(v_s[buf][hk]);
+#pragma unroll
+        for (int c = 0; c < kChunks; ++c) {
+          if ((c & 1) != half) continue;
+          cp_async_16(kd + core_off(key, c, kSboQ), ksrc + c, nb);
+          // V is the B operand of O += P V (N = head dims, K = keys), MN-major no-swizzle core matrices:
+          //   element (dim n, key) -> (n / 8) * sbo + (key / 8) * lbo + (key % 8) * 16 + (n % 8) * 2
+          cp_async_16(vd + c * kSboV + (key >> 3) * kLbo + (key & 7) * 16, vsrc + c, nb);
+        }
+      }
+      cp_async_commit();
+    } else if (k_ok_next) {
       const uint4 *ksrc = reinterpret_cast<const uint4 *>(p.k + (int64_t)krow * p.ld + (h + hk) * DP);
       const uint4 *vsrc = reinterpret_cast<const uint4 *>(p.v + (int64_t)krow * p.ldv + (h + hk) * DP);
 #pragma unroll
@@ -277,13 +298,10 @@ __global__ void __launch_bounds__(kThreads, HP == 2 ? 5 : (KB == 32 ? OS3D_ATTN_
       ph2 ^= 1;
       tc_fence_after();
     }
-    // ---- registers -> shared memory: K normalised (K-major), V transposed ----
-    if (PRENORM && key < kBlockKeys) {
-#pragma unroll
-      for (int c = 0; c < kChunks; ++c) {
-        if ((c & 1) != half) continue;
-        *reinterpret_cast<uint4 *>(k_s[hk] + core_off(key, c, kSboQ)) = k_ok_next ? k_raw[c] : make_uint4(0, 0, 0, 0);
-      }
+    const int buf = PRENORM ? (blk & 1) : 0;
+    // ---- PRENORM: this block's cp.async copies have landed; else registers -> shared memory: K normalised (K-major) ----
+    if constexpr (PRENORM) {
+      cp_async_wait<0>();
     } else if (key < kBlockKeys) {
       float f[DP];
       float ss = 0.0f;
@@ -310,10 +328,10 @@ __global__ void __launch_bounds__(kThreads, HP == 2 ? 5 : (KB == 32 ? OS3D_ATTN_
           const __nv_bfloat162 hh = __floats2bfloat162_rn(f[c * 8 + 2 * i] * inv, f[c * 8 + 2 * i + 1] * inv);
           w[i] = *reinterpret_cast<const uint32_t *>(&hh);
         }
-        *reinterpret_cast<uint4 *>(k_s[hk] + core_off(key, c, kSboQ)) = make_uint4(w[0], w[1], w[2], w[3]);
+        *reinterpret_cast<uint4 *>(k_s[0][hk] + core_off(key, c, kSboQ)) = make_uint4(w[0], w[1], w[2], w[3]);
       }
     }
-    if (key < kBlockKeys) {
+    if (!PRENORM && key < kBlockKeys) {
       // V is the B operand of O += P V with N = head dims, K = keys.  Its rows (keys) are stored as they come from
       // global memory -- 16-byte chunks of 8 dims -- in the MN-major no-swizzle core-matrix layout:
       //   element (dim n, key) -> (n / 8) * sbo + (key / 8) * lbo + (key % 8) * 16 + (n % 8) * 2
@@ -324,7 +342,7 @@ __global__ void __launch_bounds__(kThreads, HP == 2 ? 5 : (KB == 32 ? OS3D_ATTN_
         const int c = 2 * cv + half;
         if (c >= kChunks) continue;
         const uint4 u = k_ok_next ? v_raw[cv] : make_uint4(0, 0, 0, 0);
-        *reinterpret_cast<uint4 *>(v_s[hk] + c * kSboV + (key >> 3) * kLbo + (key & 7) * 16) = u;
+        *reinterpret_cast<uint4 *>(v_s[0][hk] + c * kSboV + (key >> 3) * kLbo + (key & 7) * 16) = u;
       }
     }
     if (DROP && key < kBlockKeys && half == 0 && hk == 0) krow_s[key] = krow_cur;
@@ -338,7 +356,7 @@ __global__ void __launch_bounds__(kThreads, HP == 2 ? 5 : (KB == 32 ? OS3D_ATTN_
 #pragma unroll
         for (int s = 0; s < DP / 16; ++s)
           umma_bf16(tmem_base + hh * kBlockKeys, make_kmajor_nosw_desc(smem_u32(q_s[hh]) + s * 2 * kLbo, kLbo, kSboQ),
-                    make_kmajor_nosw_desc(smem_u32(k_s[hh]) + s * 2 * kLbo, kLbo, kSboQ), idesc1, s > 0 ? 1u : 0u);
+                    make_kmajor_nosw_desc(smem_u32(k_s[buf][hh]) + s * 2 * kLbo, kLbo, kSboQ), idesc1, s > 0 ? 1u : 0u);
       umma_commit(bar1);
     }
     prefetch(blk + 1);        // global loads for the next key block fly during MMA 1, the softmax and MMA 2
@@ -473,7 +491,7 @@ __global__ void __launch_bounds__(kThreads, HP == 2 ? 5 : (KB == 32 ? OS3D_ATTN_
 #pragma unroll
         for (int s2 = 0; s2 < kBlockKeys / 16; ++s2)
           umma_bf16(tmem_o + hh * DP, make_kmajor_nosw_desc(smem_u32(p_s[hh]) + s2 * 2 * kLbo, kLbo, kSboP),
-                    make_kmajor_nosw_desc(smem_u32(v_s[hh]) + s2 * 2 * kLbo, kLbo, kSboV), idesc2, (blk > 0 || s2 > 0) ? 1u : 0u);
+                    make_kmajor_nosw_desc(smem_u32(v_s[buf][hh]) + s2 * 2 * kLbo, kLbo, kSboV), idesc2, (blk > 0 || s2 > 0) ? 1u : 0u);
       umma_commit(bar2);
     }
     if (kPT && tid == 0) {
@@ -483,7 +501,7 @@ __global__ void __launch_bounds__(kThreads, HP == 2 ? 5 : (KB == 32 ? OS3D_ATTN_
         const uint32_t v_hi_w = nosw_desc_hi(kSboV);
 #pragma unroll
         for (int s2 = 0; s2 < kBlockKeys / 16; ++s2)
-          umma_bf16_ts_acc(tmem_o, tmem_base + s2 * 8, nosw_desc_lo(smem_u32(v_s[0]) + s2 * 2 * kLbo, kLbo), v_hi_w,
+          umma_bf16_ts_acc(tmem_o, tmem_base + s2 * 8, nosw_desc_lo(smem_u32(v_s[buf][0]) + s2 * 2 * kLbo, kLbo), v_hi_w,
                            idesc2, off0, off1, off2, off3);
       }
       umma_commit(bar2);
