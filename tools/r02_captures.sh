@@ -1,11 +1,11 @@
 # ncu captures of the final round-2 kernels (one GPU; every command first runs plain, then under ncu).
-#   bash tools/r02_captures.sh            -> gpurun_out/r02m_*.ncu-rep + gpurun_out/r02m_launches.csv
+#   bash tools/r02_captures.sh            -> gpurun_out/r02n_*.ncu-rep + gpurun_out/r02n_launches.csv
 set -x
 B="python bench.py --steps 1 --warmup 3 --no-other-configs --no-cpu-baseline"
-$B > gpurun_out/plain_bench.log 2>&1 && ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none --csv --log-file gpurun_out/r02m_launches.csv $B > gpurun_out/ncu_bench.log 2>&1
+$B > gpurun_out/plain_bench.log 2>&1 && ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none --csv --log-file gpurun_out/r02n_launches.csv $B > gpurun_out/ncu_bench.log 2>&1
 cap() {  # name, kernel regex, skip, command...
   name=$1; rx=$2; skip=$3; shift 3
-  "$@" > gpurun_out/plain_$name.log 2>&1 && ncu --set full --clock-control none --import-source on -k regex:$rx -s $skip -c 1 -o gpurun_out/r02m_$name "$@" > gpurun_out/ncu_$name.log 2>&1
+  "$@" > gpurun_out/plain_$name.log 2>&1 && ncu --set full --clock-control none --import-source on -k regex:$rx -s $skip -c 1 -o gpurun_out/r02n_$name "$@" > gpurun_out/ncu_$name.log 2>&1
 }
 cap spconv_l1_48_48 spconv_tc_kernel 2 python tools/run_spconv.py 1 48 48 3
 cap spconv_l2_96_96 spconv_tc_kernel 2 python tools/run_spconv.py 2 96 96 3
@@ -13,4 +13,4 @@ cap spconv_l4_384_384 spconv_tc_kernel 2 python tools/run_spconv.py 4 384 384 3
 cap attention_l1 window_attention_tc 2 python tools/run_attention.py 1 3
 cap attention_l3 window_attention_tc 2 python tools/run_attention.py 3 3
 cap qkv_l2 qkv_proj 5 python tools/run_qkv.py 2
-ls -la gpurun_out/r02m_*
+ls -la gpurun_out/r02n_*
