@@ -70,6 +70,7 @@ struct Params {
   uint32_t idesc;
   int tiles_per_cta, sa, sb;
   int sa_log2;
+  int issuers;                // MMA-issuing warps: 2 when at most four warps gather and the CTA owns >= 2 tiles (warp 7 issues the odd tiles)
 };
 
 __global__ void __launch_bounds__(kThreads, 2) spconv_tc_kernel(const Params p) {
@@ -97,8 +98,8 @@ __global__ void __launch_bounds__(kThreads, 2) spconv_tc_kernel(const Params p) 
 
   if (tid == 0) {
     for (int s = 0; s < p.sa; ++s) { mbar_init(a_full + 8 * s, 32); mbar_init(a_empty + 8 * s, 1); }
-    for (int s = 0; s < p.sb; ++s) { mbar_init(b_full + 8 * s, 1); mbar_init(b_empty + 8 * s, 1); }
-    mbar_init(accum_bar, 1);
+    for (int s = 0; s < p.sb; ++s) { mbar_init(b_full + 8 * s, 1); mbar_init(b_empty + 8 * s, (uint32_t)p.issuers); }
+    mbar_init(accum_bar, (uint32_t)p.issuers);
     fence_barrier_init();
   }
   if (tid < kMaxTiles) masks_s[tid] = tid < ntile ? (p.dense ? 1u : __ldg(p.tile_mask + tile0 + tid)) : 0u;
@@ -120,6 +121,72 @@ __global__ void __launch_bounds__(kThreads, 2) spconv_tc_kernel(const Params p) 
 #pragma unroll
   for (int t = 0; t < kMaxTiles; ++t) any |= masks_s[t];
 
+  // ---- the MMA-issuing loop (warp 8; with two issuers also warp 7, which takes the odd tiles of the CTA) ----
+  auto issue_loop = [&](const uint32_t which) {
+    {
+      int sb_i = 0;
+      uint32_t q = 0, b_ph = 0, started = 0, ready = 0;      // q: slots consumed so far
+      // Two issuers = two independent pipelines: issuer w consumes the tiles t with (t & 1) == w out of ring slots
+      // [w sa/2, (w + 1) sa/2), filled by the gather warps of the same half.  (One shared ring would let an issuer run a
+      // whole revolution ahead of the other on a slot -- an mbarrier parity cannot tell that from "filled".)
+      const bool two_issuers = p.issuers == 2;
+      const uint32_t sa_shift = (uint32_t)p.sa_log2 - (two_issuers ? 1u : 0u), sa_mask = (1u << sa_shift) - 1u;
+      const uint32_t slot0 = two_issuers ? which << sa_shift : 0u;
+      const uint32_t tmask = two_issuers ? (which ? 0xaaaaaaaau : 0x55555555u) : 0xffffffffu;
+      const uint32_t desc_hi = (uint32_t)(make_kmajor_sw128_desc(0) >> 32);
+      const uint32_t a_lo0 = (uint32_t)make_kmajor_sw128_desc(a_base), b_lo0 = (uint32_t)make_kmajor_sw128_desc(b_base);
+      const uint32_t b_step = (uint32_t)b_bytes >> 4, part_lo = (uint32_t)(p.n_per_part * 128) >> 4;
+      const bool two_parts = p.n_parts == 2;
+      const uint32_t idesc = p.idesc, cout = (uint32_t)p.cout, npp = (uint32_t)p.n_per_part;
+      const int last_steps = (p.cin16 - (p.ncb - 1) * kBlockK) >> 4;
+      for (int k = 0; k < OS3D_KVOL; ++k) {
+        if (!((any >> k) & 1u)) continue;
+        uint32_t tiles_k = 0;                              // tiles of this CTA that have offset k
+        for (int t = 0; t < ntile; ++t) tiles_k |= ((masks_s[t] >> k) & 1u) << t;
+        tiles_k = __shfl_sync(0xffffffffu, tiles_k, 0);
+        for (int cb = 0; cb < p.ncb; ++cb) {
+          const int steps = cb + 1 < p.ncb ? kBlockK / 16 : last_steps;
+          mbar_wait(b_full + 8 * sb_i, b_ph);
+          const uint32_t b_lo = b_lo0 + sb_i * b_step;
+          for (uint32_t rem = tiles_k & tmask; rem; rem &= rem - 1) {
+            const uint32_t t = __ffs(rem) - 1;
+            const uint32_t slot = slot0 + (q & sa_mask);
+            if (!ready) mbar_wait(a_full + 8 * slot, (q >> sa_shift) & 1u);
+            // probe the NEXT slot's barrier now: its round trip overlaps the MMAs issued below
+            ready = mbar_test(a_full + 8 * (slot0 + ((q + 1) & sa_mask)), ((q + 1) >> sa_shift) & 1u);
+            fence_proxy_async();   // LDGSTS (generic proxy) writes observed through the barrier -> visible to the MMA's async proxy
+            tc_fence_after();
+            const uint32_t a_lo = a_lo0 + slot * (kATileBytes >> 4);
+            const uint32_t d = tmem_base + t * cout;
+            const uint32_t acc0 = (started >> t) & 1u;
+            if (elect_one()) {
+              umma_bf16_lo(d, a_lo, b_lo, desc_hi, idesc, acc0);
+              if (two_parts) umma_bf16_lo(d + npp, a_lo, b_lo + part_lo, desc_hi, idesc, acc0);
+#pragma unroll
+              for (int ks = 1; ks < kBlockK / 16; ++ks) {
+                if (ks < steps) {
+                  umma_bf16_lo(d, a_lo + 2 * ks, b_lo + 2 * ks, desc_hi, idesc, 1u);
+                  if (two_parts) umma_bf16_lo(d + npp, a_lo + 2 * ks, b_lo + part_lo + 2 * ks, desc_hi, idesc, 1u);
+                }
+              }
+              umma_commit(a_empty + 8 * slot);
+            }
+            __syncwarp();
+            started |= 1u << t;
+            ++q;
+          }
+          if (elect_one()) umma_commit(b_empty + 8 * sb_i);
+          __syncwarp();
+          if (++sb_i == p.sb) { sb_i = 0; b_ph ^= 1; }
+        }
+      }
+      if (elect_one()) {
+        if (started) umma_commit(accum_bar);
+        else mbar_arrive(accum_bar);
+      }
+    }
+  };
+
   if (warp < kEpiWarps) {
     // ================================ producers ================================
     // A full / empty mbarrier round trip costs ~300 cycles per thread (tools/bench_mbar.cu), whatever the ring depth:
@@ -131,8 +198,11 @@ __global__ void __launch_bounds__(kThreads, 2) spconv_tc_kernel(const Params p) 
     // the row of iteration i is then a warp shuffle away.  Completion: cp.async.mbarrier.arrive.noinc (32 per slot).
     if (warp < p.sa) {
       const uint32_t c = lane & 7, g = lane >> 3;
-      const uint32_t nprod_mask = (uint32_t)p.sa - 1u;
-      const uint32_t slot = (uint32_t)warp;
+      // (two issuers: the warps of each half of the ring serve one issuer's tiles -- even tiles, odd tiles)
+      const bool two_issuers = p.issuers == 2;
+      const uint32_t nprod_mask = ((uint32_t)p.sa >> (two_issuers ? 1 : 0)) - 1u;
+      const uint32_t slot = (uint32_t)warp, slot_g = (uint32_t)warp & nprod_mask;          // ring slot; index inside the half
+      const uint32_t tmask = two_issuers ? (((uint32_t)warp > nprod_mask) ? 0xaaaaaaaau : 0x55555555u) : 0xffffffffu;
       const uint32_t dst_base = a_base + slot * kATileBytes + g * 32 * 128;
       const uint32_t full_bar = a_full + 8 * slot, empty_bar = a_empty + 8 * slot;
       const char *in_bytes = reinterpret_cast<const char *>(p.in);
@@ -157,9 +227,10 @@ __global__ void __launch_bounds__(kThreads, 2) spconv_tc_kernel(const Params p) 
             } while (!((any >> ik) & 1u));
             tiles_k = 0;
             for (int t = 0; t < ntile; ++t) tiles_k |= ((masks_s[t] >> ik) & 1u) << t;
+            tiles_k &= tmask;
             cnt = __popc(tiles_k);
           }
-          r = (slot - u0) & nprod_mask;
+          r = (slot_g - u0) & nprod_mask;
         }
       };
       auto fetch_rows = [&]() -> int4 {
@@ -195,6 +266,9 @@ __global__ void __launch_bounds__(kThreads, 2) spconv_tc_kernel(const Params p) 
         }
         cp_async_mbar_arrive_noinc(full_bar);
       }
+    } else if (p.issuers == 2 && warp == kEpiWarps - 1) {
+      issue_loop(1);          // second MMA issuer: the serial per-slot work (wait, proxy fence, issue, commit) of the odd tiles
+      __syncwarp();
     }
   } else if (warp == kEpiWarps + 1) {
     // ================================ weight loader ================================
@@ -220,62 +294,7 @@ __global__ void __launch_bounds__(kThreads, 2) spconv_tc_kernel(const Params p) 
     // the first version: 130 instructions per slot, tensor pipe 11 % busy, producers blocked on empty slots).  The loop
     // is therefore stripped to: barrier wait, fence, 1-8 UTCHMMA whose descriptors differ only in their low word, commit.
     // The WHOLE warp runs this loop on warp-uniform values; only the tcgen05 instructions are under elect.sync.
-    {
-      int sb_i = 0;
-      uint32_t q = 0, b_ph = 0, started = 0, ready = 0;      // q: slots consumed so far
-      const uint32_t sa_mask = (uint32_t)p.sa - 1u, sa_shift = (uint32_t)p.sa_log2;
-      const uint32_t desc_hi = (uint32_t)(make_kmajor_sw128_desc(0) >> 32);
-      const uint32_t a_lo0 = (uint32_t)make_kmajor_sw128_desc(a_base), b_lo0 = (uint32_t)make_kmajor_sw128_desc(b_base);
-      const uint32_t b_step = (uint32_t)b_bytes >> 4, part_lo = (uint32_t)(p.n_per_part * 128) >> 4;
-      const bool two_parts = p.n_parts == 2;
-      const uint32_t idesc = p.idesc, cout = (uint32_t)p.cout, npp = (uint32_t)p.n_per_part;
-      const int last_steps = (p.cin16 - (p.ncb - 1) * kBlockK) >> 4;
-      for (int k = 0; k < OS3D_KVOL; ++k) {
-        if (!((any >> k) & 1u)) continue;
-        uint32_t tiles_k = 0;                              // tiles of this CTA that have offset k
-        for (int t = 0; t < ntile; ++t) tiles_k |= ((masks_s[t] >> k) & 1u) << t;
-        tiles_k = __shfl_sync(0xffffffffu, tiles_k, 0);
-        for (int cb = 0; cb < p.ncb; ++cb) {
-          const int steps = cb + 1 < p.ncb ? kBlockK / 16 : last_steps;
-          mbar_wait(b_full + 8 * sb_i, b_ph);
-          const uint32_t b_lo = b_lo0 + sb_i * b_step;
-          for (uint32_t rem = tiles_k; rem; rem &= rem - 1) {
-            const uint32_t t = __ffs(rem) - 1;
-            const uint32_t slot = q & sa_mask;
-            if (!ready) mbar_wait(a_full + 8 * slot, (q >> sa_shift) & 1u);
-            // probe the NEXT slot's barrier now: its round trip overlaps the MMAs issued below
-            ready = mbar_test(a_full + 8 * ((q + 1) & sa_mask), ((q + 1) >> sa_shift) & 1u);
-            fence_proxy_async();   // LDGSTS (generic proxy) writes observed through the barrier -> visible to the MMA's async proxy
-            tc_fence_after();
-            const uint32_t a_lo = a_lo0 + slot * (kATileBytes >> 4);
-            const uint32_t d = tmem_base + t * cout;
-            const uint32_t acc0 = (started >> t) & 1u;
-            if (elect_one()) {
-              umma_bf16_lo(d, a_lo, b_lo, desc_hi, idesc, acc0);
-              if (two_parts) umma_bf16_lo(d + npp, a_lo, b_lo + part_lo, desc_hi, idesc, acc0);
-#pragma unroll
-              for (int ks = 1; ks < kBlockK / 16; ++ks) {
-                if (ks < steps) {
-                  umma_bf16_lo(d, a_lo + 2 * ks, b_lo + 2 * ks, desc_hi, idesc, 1u);
-                  if (two_parts) umma_bf16_lo(d + npp, a_lo + 2 * ks, b_lo + part_lo + 2 * ks, desc_hi, idesc, 1u);
-                }
-              }
-              umma_commit(a_empty + 8 * slot);
-            }
-            __syncwarp();
-            started |= 1u << t;
-            ++q;
-          }
-          if (elect_one()) umma_commit(b_empty + 8 * sb_i);
-          __syncwarp();
-          if (++sb_i == p.sb) { sb_i = 0; b_ph ^= 1; }
-        }
-      }
-      if (elect_one()) {
-        if (started) umma_commit(accum_bar);
-        else mbar_arrive(accum_bar);
-      }
-    }
+    issue_loop(0);
     __syncwarp();
   }
   if (warp < kEpiWarps) {
@@ -630,6 +649,10 @@ static int launch_tc(tc::Params &p, cudaStream_t stream) {
   p.sa = sa;
   p.sa_log2 = sa_log2;
   p.sb = sb;
+  // One issuing warp's serial per-slot work (barrier wait, proxy fence, UTCHMMAs, commit: ~500 cycles) paces the layers with
+  // several small tiles per CTA; when warps 4-7 do not gather, warp 7 issues the odd tiles.  (OS3D_SPCONV_ISSUERS=1: off)
+  p.issuers = (sa <= 4 && tiles >= 2) ? 2 : 1;
+  { const char *e = getenv("OS3D_SPCONV_ISSUERS"); if (e && atoi(e) == 1) p.issuers = 1; }
   const int smem = 1024 + sa * tc::kATileBytes + sb * b_bytes + tail;
   // the opt-in to > 48 KB of dynamic shared memory is a per-device attribute: once per device, not once per process
   static bool configured[64] = {false};
