@@ -52,25 +52,47 @@ def workload_config(config, frames, n_points, world):
 
 
 class ClockSampler(threading.Thread):
-    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    """SM clocks / throttle reasons during the timed region (B200_PROFILING.md recipe).  Read through NVML in-process
+    (nvidia_ml_py): a `nvidia-smi` subprocess per sample initialises the driver's management library every time and
+    was seen to stall kernel launches of the timed steps for milliseconds (one step in ten at 46-50 ms instead of
+    42.5); the subprocess query stays as the fallback when NVML cannot be loaded."""
     Q = ('clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,'
          'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap')
 
     def __init__(self, index):
         super().__init__(daemon=True)
         self.index, self.rows, self.stop_flag = index, [], False
+        self.nvml = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.handle = pynvml.nvmlDeviceGetHandleByIndex(int(index))
+            self.max_sm = float(pynvml.nvmlDeviceGetMaxClockInfo(self.handle, pynvml.NVML_CLOCK_SM))
+            self.nvml = pynvml
+        except Exception:
+            self.nvml = None
+
+    def _sample_nvml(self):
+        n = self.nvml
+        sm = float(n.nvmlDeviceGetClockInfo(self.handle, n.NVML_CLOCK_SM))
+        bits = int(n.nvmlDeviceGetCurrentClocksThrottleReasons(self.handle))
+        act = lambda mask: 'Active' if bits & mask else 'Not Active'      # noqa: E731
+        return [str(sm), str(self.max_sm), act(0x8), act(0x40), act(0x20), act(0x4)]    # hw, hw thermal, sw thermal, sw power cap
 
     def run(self):
         while not self.stop_flag:
             try:
-                out = subprocess.run(['nvidia-smi', '-i', str(self.index), f'--query-gpu={self.Q}',
-                                      '--format=csv,noheader,nounits'], capture_output=True, text=True, timeout=5).stdout
-                f = [x.strip() for x in out.strip().split(',')]
-                if len(f) == 6:
-                    self.rows.append(f)
+                if self.nvml is not None:
+                    self.rows.append(self._sample_nvml())
+                else:
+                    out = subprocess.run(['nvidia-smi', '-i', str(self.index), f'--query-gpu={self.Q}',
+                                          '--format=csv,noheader,nounits'], capture_output=True, text=True, timeout=5).stdout
+                    f = [x.strip() for x in out.strip().split(',')]
+                    if len(f) == 6:
+                        self.rows.append(f)
             except Exception:
-                pass
-            time.sleep(0.1)
+                self.nvml = None              # NVML failed mid-run: fall back to the subprocess query
+            time.sleep(0.05 if self.nvml is not None else 0.1)
 
     def summary(self):
         if not self.rows:
@@ -79,7 +101,7 @@ class ClockSampler(threading.Thread):
         names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
         reasons = [n for i, n in enumerate(names) if any(r[2 + i] == 'Active' for r in self.rows)]
         return {'sm_mhz': sm[len(sm) // 2], 'sm_max_mhz': float(self.rows[0][1]), 'reasons': reasons,
-                'samples': len(self.rows)}
+                'samples': len(self.rows), 'source': 'nvml' if self.nvml is not None else 'nvidia-smi'}
 
 
 # ------------------------------------------------------------------------------------------------------------------
