@@ -482,7 +482,16 @@ __global__ void __launch_bounds__(kThreads, 2) spconv_tc_kernel(const Params p) 
 // in L2.  The sort is one cub radix sort of 32-bit keys (block << 27 | mask) with the row index as value.
 constexpr int kOrderRowsPerCta = 256;
 
-// sort key of every row: (block of consecutive rows) << 27 | 27-bit offset mask; coalesced reads of the row-major map
+// Significance of the 27 offsets in the sort key, least significant first: the centre, the in-plane axis neighbours, the
+// in-plane diagonals, the two vertical neighbours, the vertical edges, the corners -- i.e. by falling frequency in lidar
+// maps (a submanifold map is symmetric, k and 26 - k are equally frequent; the ranking is the same at every level).  With
+// the RARE offsets in the high key bits, rows that lack them end up in the same tiles and those tiles skip the offsets:
+// 13.97 -> 12.35 active offsets per 128-row tile at level 1, 19.81 -> 19.30 at level 2, strided maps 9.19 -> 8.83 /
+// 15.49 -> 14.75, inverse maps unchanged at 3.4 (CPU simulation on the oracle's maps of two frames, tools/sim_tile_order.py).
+__constant__ int8_t kOrderBit[OS3D_KVOL] = {13, 10, 12, 14, 16, 9, 11, 15, 17, 4, 22, 1, 3, 5, 7, 19, 21, 23, 25, 0, 2, 6, 8, 18, 20, 24, 26};
+
+// sort key of every row: (block of consecutive rows) << 27 | 27-bit offset mask, bits permuted as above; coalesced reads of
+// the row-major map
 __global__ void __launch_bounds__(256) order_keys_kernel(const int32_t *__restrict__ nbr, int64_t m, int block_shift,
                                                          uint32_t *__restrict__ keys, int32_t *__restrict__ rows) {
   __shared__ uint32_t bits_s[kOrderRowsPerCta];
@@ -497,7 +506,11 @@ __global__ void __launch_bounds__(256) order_keys_kernel(const int32_t *__restri
   __syncthreads();
   if ((int)threadIdx.x < n) {
     const int64_t r = row0 + threadIdx.x;
-    keys[r] = ((uint32_t)(r >> block_shift) << OS3D_KVOL) | bits_s[threadIdx.x];
+    const uint32_t mask = bits_s[threadIdx.x];
+    uint32_t key = 0;
+#pragma unroll
+    for (int j = 0; j < OS3D_KVOL; ++j) key |= ((mask >> kOrderBit[j]) & 1u) << j;
+    keys[r] = ((uint32_t)(r >> block_shift) << OS3D_KVOL) | key;
     rows[r] = (int32_t)r;
   }
 }
@@ -558,8 +571,13 @@ __global__ void pack_weight_img_kernel(const float *__restrict__ src, int cin, i
 
 using namespace os3d;
 
-static int order_block_shift(int64_t m) {     // blocks of >= 65536 rows, at most 32 of them (5 key bits above the mask)
-  int shift = 16;
+// Blocks of >= 262144 rows, at most 32 of them (5 key bits above the mask).  Measured on the 8-frame batch (conv time per
+// step): 64 k rows 11.71 ms, 256 k rows 11.37, 512 k 11.39, 1 M 11.40 -- larger blocks group the masks better (level 1:
+// 12.35 -> 10.75 active offsets per tile) until the gathers of concurrent CTAs stop sharing L2 lines (the 384-channel
+// inverse conv loses 5 % at 1 M rows).
+static int order_block_shift(int64_t m) {
+  int shift = 18;
+  { const char *e = getenv("OS3D_ORDER_BLOCK_SHIFT"); if (e && atoi(e) >= 10 && atoi(e) <= 30) shift = atoi(e); }
   while ((m >> shift) >= 32) ++shift;
   return shift;
 }
