@@ -476,8 +476,9 @@ __global__ void __launch_bounds__(kThreads, 2) spconv_tc_kernel(const Params p) 
 // ---- tile order of a kernel map --------------------------------------------------------------------------------
 // An output-stationary tile does the MMAs of every offset that ANY of its 128 rows has, so rows with the same set of
 // neighbour offsets should share tiles.  In storage order a tile of the synthetic Waymo frames has 24.9 (L1 subm) /
-// 26.6 (inverse convs) of the 27 offsets; sorted by mask (lexicographic: similar masks end up adjacent) inside blocks of
-// 65536 consecutive rows it has 13.8 / 3.4 (the inverse conv's rows fall into the 8 parity classes).  Blocks, not a
+// 26.6 (inverse convs) of the 27 offsets; sorted by mask (similar masks end up adjacent) inside blocks of consecutive rows
+// it has 13.8 / 3.4 with 64 k-row blocks and the plain mask as key, 10.8 / 3.4 with 256 k-row blocks and the
+// frequency-ranked bit order below (the inverse conv's rows fall into the 8 parity classes either way).  Blocks, not a
 // global sort, keep the gather local: a tile's neighbours stay within a window of rows that the concurrent CTAs share
 // in L2.  The sort is one cub radix sort of 32-bit keys (block << 27 | mask) with the row index as value.
 constexpr int kOrderRowsPerCta = 256;
