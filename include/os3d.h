@@ -133,11 +133,11 @@ int os3d_strided_tables(const int32_t *idx, int64_t m, int sz, int sy, int sx, c
  * replaces: SubMConv3d / SparseConv3d / SparseInverseConv3d forward (spconv-cu113; seg3d/utils/spconv_utils.py:16-22). */
 int os3d_spconv_fwd_f32(const float *in, const int32_t *nbr, int64_t m_out, int cin, int cout, const float *w,
                         const float *bias, float *out, void *stream);
-/* Tile order of a kernel map: perm [m] lists the output rows sorted by their set of neighbour offsets (the 27-bit mask,
- * lexicographic, so similar sets are adjacent) inside blocks of >= 65536 consecutive rows, so that the rows of a 128-row
- * tile share offsets and the tensor-core kernel skips the others (storage order: ~25 of 27 offsets per tile; sorted: 3.4
- * for inverse convs, 13.8 for the level-1 submanifold map).  Blocks keep the gather L2-local.  Results do not depend on
- * the order.  keys, keys_sorted, rows: [m] scratch; temp: os3d_kernel_map_order_scratch(m) bytes (radix sort). */
+/* Tile order of a kernel map: perm [m] lists the output rows sorted by their set of neighbour offsets (the 27-bit mask
+ * with the rare offsets -- corners, vertical edges -- in the high key bits, so similar sets are adjacent) inside blocks of
+ * >= 262144 consecutive rows, so that the rows of a 128-row tile share offsets and the tensor-core kernel skips the others
+ * (storage order: ~25 of 27 offsets per tile; sorted: 3.4 for inverse convs, 10.8 for the level-1 submanifold map).  Blocks
+ * keep the gather L2-local.  Results do not depend on the order.  keys, keys_sorted, rows: [m] scratch; temp: os3d_kernel_map_order_scratch(m) bytes (radix sort). */
 int os3d_kernel_map_order_scratch(int64_t m, int64_t *temp_bytes);
 int os3d_kernel_map_order(const int32_t *nbr, int64_t m, uint32_t *keys, uint32_t *keys_sorted, int32_t *rows,
                           int32_t *perm, void *temp, int64_t temp_bytes, void *stream);
