@@ -63,3 +63,18 @@ def test_dense_kernel_planners_on_cpu():
     assert not MlpChain.fits([(512, 64), (64, 512)])                  # wider than a tensor-memory accumulator
     assert not MlpChain.fits([(384, 192), (192, 384)])                # weights beyond shared memory
     assert not MlpChain.fits([(128, 64), (64, 96)])                   # widths do not chain
+
+
+def test_tile_order_simulation_uses_the_kernels_bit_order():
+    """tools/sim_tile_order.py (the CPU simulation behind the conv tile order) and order_keys_kernel rank the 27 offsets
+    identically, and the ranking is a permutation that keeps the symmetric pairs (k, 26 - k) adjacent in significance."""
+    import os
+    import re
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    cu = open(os.path.join(root, 'openseg3d_b200', 'csrc', 'spconv_tc.cu')).read()
+    sim = open(os.path.join(root, 'tools', 'sim_tile_order.py')).read()
+    k_cu = [int(x) for x in re.search(r'kOrderBit\[OS3D_KVOL\] = \{([^}]*)\}', cu).group(1).split(',')]
+    k_sim = [int(x) for x in re.search(r'ORDER=\[([^\]]*)\]', sim).group(1).split(',')]
+    assert k_cu == k_sim and sorted(k_cu) == list(range(27)) and k_cu[0] == 13
+    pos = {k: i for i, k in enumerate(k_cu)}
+    assert all(abs(pos[k] - pos[26 - k]) <= 7 for k in range(27))          # a pair sits in the same frequency class
